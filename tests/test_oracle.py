@@ -1,0 +1,148 @@
+"""CPU: pin the float64 oracle (oracle/) against reference-generated golden vectors and,
+when built, against the reference's own math_module.c (oracle/_ref)."""
+import numpy as np
+import pytest
+
+from oracle import f64, hist, ref
+import synth
+
+
+def relmax(a, b):
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - b)) / np.max(np.abs(b)))
+
+
+def test_example_1A_point_field_known_answer(golden):
+    g = golden("example_1A_point_field.npz")
+    e = f64.field_grid(g["point"][None, :], g["x"], g["Q"], soften=False)[0]
+    # the shipped examples/1A_point-field/outdir/point_field.dat reproduces digit for digit
+    np.testing.assert_allclose(g["field"], g["shipped_point_field_dat"], rtol=0, atol=5e-7)
+    np.testing.assert_allclose(e, g["field"].astype(np.float64), rtol=2e-5)
+
+
+def test_example_2A_volume(golden):
+    g = golden("example_2A_volume.npz")
+    pts = g["mesh"].reshape(-1, 3)
+    fb = g["field_box"]
+    assert fb.shape == (1331, 6) and fb.dtype == np.float32
+    np.testing.assert_array_equal(fb[:, :3], pts)
+    e = f64.field_grid(pts, g["x"], g["Q"], soften=True)
+    assert relmax(fb[:, 3:], e) < 1e-5
+
+
+def test_example_2A_volume_esp(golden):
+    g = golden("example_2A_volume.npz")
+    ge = golden("example_2A_volume_esp.npz")
+    pts = ge["mesh"].reshape(-1, 3)
+    phi = f64.esp_grid(pts, g["x"], g["Q"])
+    # the reference sums 7,890 cancelling terms sequentially in FP32: its own deviation from
+    # float64 is ~4e-5 of the max-norm here (the float64 restatement is the truth, not it)
+    assert relmax(ge["esp_f32"], phi) < 2e-4
+    # the calculator-level return is float16 [coords | ESP]  (UC:473-475)
+    box = ge["esp_box"]
+    assert box.dtype == np.float16 and box.shape == (1331, 4)
+    np.testing.assert_array_equal(box[:, :3], pts.astype(np.float16))
+    np.testing.assert_array_equal(box[:, 3], ge["esp_f32"].astype(np.float64).astype(np.float16))
+    ulp16 = np.spacing(np.abs(box[:, 3]).astype(np.float16)).astype(np.float64)
+    assert np.all(np.abs(box[:, 3].astype(np.float64) - phi) <= 0.5 * ulp16 + 2e-4 * np.max(np.abs(phi)))
+
+
+def test_example_3A_topo(golden):
+    g = golden("example_2A_volume.npz")
+    t = golden("example_3A_topo.npz")
+    out, steps = f64.topo_batch(t["seeds"], t["n_iter"], g["x"], g["Q"], float(t["step_size"]),
+                                t["dimensions"])
+    h = float(t["step_size"])
+    assert np.max(np.abs(out[:, 0] - t["hist"][:, 0])) < 2e-6
+    # FP32 second differences: reference-vs-float64 noise ~1e-7/h^2
+    assert np.max(np.abs(out[:, 1] - t["hist"][:, 1])) < 5e-5 + 2e-7 / h**2
+    assert np.all(steps <= t["n_iter"]) and np.all(steps >= 1)
+
+
+def test_synthetic_math_ops(golden):
+    g = golden("synthetic_math_ops.npz")
+    x, Q, pts = g["x"], g["Q"], g["points"]
+    e_soft = f64.field_grid(pts, x, Q, soften=True)
+    e_raw = f64.field_grid(pts, x, Q, soften=False)
+    assert relmax(g["looped_field"], e_soft) < 1e-5
+    assert relmax(g["calc_field"], e_raw) < 1e-5
+    assert relmax(g["calc_field_base"], e_raw) < 1e-5
+    assert relmax(g["esp"], f64.esp_grid(pts, x, Q)) < 1e-4
+    # softening max(r^2, 1e-6): a point sitting on a charge gives a finite field (C:433)
+    es = f64.field_grid(g["points_soft"], x, Q, soften=True)
+    assert np.all(np.isfinite(es))
+    assert relmax(g["looped_field_soft"], es) < 1e-5
+    for h in (0.1, 0.01):
+        out, _ = f64.topo_batch(g["seeds"], g[f"n_iter_h{h}"], x, Q, h, g["dimensions"])
+        ref_lines = g[f"lines_h{h}"]
+        flips = np.abs(out[:, 0] - ref_lines[:, 0]) > h / 2
+        assert flips.mean() <= 0.05
+        ok = ~flips
+        assert np.max(np.abs(out[ok, 0] - ref_lines[ok, 0])) < 5e-6
+        assert np.max(np.abs(out[ok, 1] - ref_lines[ok, 1])) < 5e-5 + 2e-7 / h**2
+
+
+def test_seed_and_mesh_generators(golden):
+    g = golden("seeds_mesh.npz")
+    d = g["dims"]
+    m = g["mesh_inclusive"]
+    assert m.shape == (5, 7, 9, 3)
+    np.testing.assert_allclose(m[:, 0, 0, 0], np.linspace(-d[0], d[0], 5), rtol=1e-7)
+    np.testing.assert_allclose(m[0, 0, :, 2], np.linspace(-d[2], d[2], 9), rtol=1e-7)
+    s = g["seeds_uniform"]
+    np.testing.assert_allclose(s[:, 0, 0, 0], np.linspace(-d[0], d[0], 6, endpoint=False)[1:], rtol=1e-6)
+    np.testing.assert_array_equal(g["n_iter_seed42_max27"],
+                                  np.random.RandomState(42).randint(1, 27, 125))
+    # tests/synth.py follows the same rules
+    sg, n_iter, dims, max_steps = synth.seeds(5, 0.5, 0.1)
+    assert max_steps == 17 and sg.shape == (125, 3) and n_iter.min() >= 1 and n_iter.max() < 17
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+def test_oracle_vs_compiled_reference():
+    x, Q = synth.charges(3000, seed=3, box=1.0)
+    pts = synth.grid(5, 1.0)
+    assert relmax(ref.compute_looped_field(pts, x, Q), f64.field_grid(pts, x, Q, True)) < 1e-5
+    assert relmax(ref.field_grid(pts, x, Q, threads=4), f64.field_grid(pts, x, Q, True)) < 1e-5
+    assert relmax(ref.esp_grid(pts[:40], x, Q, threads=2), f64.esp_grid(pts[:40], x, Q)) < 1e-4
+    e = np.array([ref.calc_field_base(p, x, Q) for p in pts[:20]])
+    assert relmax(e, f64.field_grid(pts[:20], x, Q, False)) < 1e-5
+    seeds, n_iter, dims, _ = synth.seeds(4, 1.0, 0.1)
+    a = ref.topo(seeds, n_iter, x, Q, 0.1, dims, threads=4)
+    b, steps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
+    assert np.max(np.abs(a[:, 0] - b[:, 0])) < 5e-6
+    assert np.max(np.abs(a[:, 1] - b[:, 1])) < 5e-5 + 2e-7 / 0.01
+    # single-line entry point agrees with the batch entry point
+    r1, k1 = f64.line(seeds[5], n_iter[5], x, Q, 0.1, dims)
+    np.testing.assert_array_equal(r1, b[5])
+    assert k1 == steps[5]
+
+
+def test_histogram_restatement_is_numpy_bit_exact():
+    rng = np.random.default_rng(0)
+    d = rng.gamma(2.0, 0.3, 20000).astype(np.float32).astype(np.float64)
+    c = rng.gamma(1.5, 0.4, 20000).astype(np.float32).astype(np.float64)
+    for nd, nc, dr, cr in [(50, 50, (0.0, d.max()), (0.0, c.max())),
+                           (37, 91, (d.min(), d.max()), (c.min(), c.max())),
+                           (8, 5, (0.2, 0.9), (0.1, 2.0))]:     # outliers on both sides
+        mine = hist.hist2d_counts(d, c, nd, nc, dr, cr)
+        theirs, _, _ = np.histogram2d(d, c, bins=[nd, nc], range=[dr, cr])
+        np.testing.assert_array_equal(mine, theirs.astype(np.int64))
+    # edge values: exactly on inner edges and on the right-most edge
+    ed = hist.edges(0.0, 1.0, 10)
+    dd = np.concatenate([ed, ed])
+    cc = np.concatenate([ed, ed[::-1]])
+    mine = hist.hist2d_counts(dd, cc, 10, 10, (0.0, 1.0), (0.0, 1.0))
+    theirs, _, _ = np.histogram2d(dd, cc, bins=[10, 10], range=[(0.0, 1.0), (0.0, 1.0)])
+    np.testing.assert_array_equal(mine, theirs.astype(np.int64))
+
+
+def test_chi2_distance():
+    rng = np.random.default_rng(1)
+    a = rng.random(100); a[:10] = 0; a /= a.sum()
+    b = rng.random(100); b[:20] = 0; b /= b.sum()
+    assert hist.chi2(a, a) == 0.0
+    s = a + b
+    expect = 0.5 * np.sum(((a - b) ** 2)[s != 0] / s[s != 0])
+    assert abs(hist.chi2(a, b) - expect) < 1e-15
+    Mx = hist.chi2_matrix(np.stack([a, b, a]))
+    assert Mx[0, 2] == 0 and Mx[0, 1] == Mx[1, 0] == hist.chi2(a, b)
