@@ -1,0 +1,183 @@
+/*
+ * cpet_b200.h -- C ABI of libcpetb200.so, the B200 (sm_100a) drop-in for PyCPET's C-shared
+ * math module on the Coulomb field / ESP / streamline / histogram hot path.
+ *
+ * The reference loads `CPET/utils/math_module.c` with ctypes.CDLL (CPET/utils/c_ops.py:9-12,
+ * CPET/utils/calculator.py:19-29) and calls it with plain `float *` / `int` arguments.  This library is
+ * opened the same way.  It exports
+ *
+ *   (A) the reference's legacy symbols with identical names, argument order and ownership rules
+ *       (caller allocates every output; nothing is retained), so `Math_ops(shared_loc=...)`
+ *       constructs and runs unchanged on top of it; and
+ *   (B) batched `cpet_*` entry points (one call per grid / per frame of streamlines / per batch
+ *       of histograms) that the calculator-level functions should call instead of looping over
+ *       points or forking a Pool.  Each has a host-pointer form and a `_dev` form taking device
+ *       pointers (the latter never synchronises and runs on the context's stream).
+ *
+ * Plain pointers and sizes only; no torch / numpy types cross this boundary.
+ * There is NO CPU fallback: every entry point runs hand-written CUDA kernels, and fails (status
+ * code < 0, or for the `void` legacy symbols: NaN-filled outputs + cpet_last_status() < 0 + a
+ * message on stderr) when no sm_100-class device is usable.
+ *
+ * Reference citations use C = CPET/utils/math_module.c, OPS = CPET/utils/c_ops.py,
+ * UC = CPET/utils/calculator.py, SC = CPET/source/calculator.py, GPU = CPET/utils/gpu.py.
+ */
+#ifndef CPET_B200_H
+#define CPET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPET_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- status / errors ---------- */
+#define CPET_OK 0
+#define CPET_ERR_INVALID (-1)   /* bad argument (null pointer, negative size, unknown flag)      */
+#define CPET_ERR_CUDA (-2)      /* CUDA runtime/driver error, see cpet_last_error()               */
+#define CPET_ERR_NO_DEVICE (-3) /* no CUDA device, or device is not compute capability 10.x       */
+#define CPET_ERR_STATE (-4)     /* call order: e.g. field requested before cpet_set_charges()     */
+
+int cpet_abi_version(void);
+/* Thread-local message / status of the most recent failing call on this thread ("" / 0 if none). */
+const char *cpet_last_error(void);
+int cpet_last_status(void);
+void cpet_clear_error(void);
+int cpet_device_count(void);
+
+/* ---------------------------------------------------------------- contexts ----------------- */
+/* A context = one device + one stream + the resident packed charge set of the current frame +
+ * grow-only scratch.  Not thread-safe; use one per host thread / per GPU. */
+typedef struct cpet_ctx cpet_ctx;
+
+int cpet_create(int device, cpet_ctx **out);
+/* Borrow an existing CUstream/cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream). */
+int cpet_create_on_stream(int device, void *cuda_stream, cpet_ctx **out);
+int cpet_destroy(cpet_ctx *ctx);
+int cpet_sync(cpet_ctx *ctx);
+int cpet_device_of(cpet_ctx *ctx);
+/* Tuning knobs for experiments: key in {"k1_threads","k1_points","k1_lanes","k1_tile_pairs",
+ * "k1_stages","k2_threads","k2_lanes","k2_tile_pairs","k2_stages","k2_ctas_per_sm","k2_sort"};
+ * value <= 0 restores the built-in heuristic. */
+int cpet_set_tuning(cpet_ctx *ctx, const char *key, int value);
+/* Counters of the last kernel-launching call: [0]=kernels launched, [1]=pair evaluations
+ * (algorithmic: points x charges, or sum over lines of (K+2) x charges), [2]=field evaluations. */
+int cpet_last_counters(cpet_ctx *ctx, int64_t out[3]);
+
+/* Upload (and pack) the charge set of one frame: x (M,3) float32 row-major, Q (M,) float32 --
+ * the `x`, `Q` arguments every reference entry point takes (OPS:250-375).  Done once per frame;
+ * all following calls on this context use it. */
+int cpet_set_charges(cpet_ctx *ctx, int n_charges, const float *x, const float *Q);
+int cpet_set_charges_dev(cpet_ctx *ctx, int n_charges, const float *d_x, const float *d_Q);
+
+/* ---------------------------------------------------------------- K1: grids ---------------- */
+#define CPET_FIELD_SOFTEN 1u  /* r^2 := max(r^2, 1e-6) as compute_looped_field (C:407,433)         */
+#define CPET_OUT_CONCAT 2u    /* field: (N,6) f32 rows [x0|E] (UC:446-447)                          */
+                              /* esp:   (N,4) f16 rows [x0|phi] (UC:473-475)                        */
+
+/* E(p_i) = k sum_j q_j (p_i - x_j)/|p_i - x_j|^3, k = 14.3996451 (C:412).
+ * Replaces compute_looped_field (C:405-451; with CPET_FIELD_SOFTEN) and per-point loops over
+ * calc_field / calc_field_base (C:255-333; without).  x0: (N,3) f32.  out: (N,3) f32, or (N,6)
+ * f32 with CPET_OUT_CONCAT. */
+int cpet_field_grid(cpet_ctx *ctx, int n_points, const float *x0, unsigned flags, float *out);
+int cpet_field_grid_dev(cpet_ctx *ctx, int n_points, const float *d_x0, unsigned flags,
+                        float *d_out);
+
+/* phi(p_i) = k sum_j q_j/|p_i - x_j| (no softening).  Replaces the Python loop over
+ * calc_esp_base in compute_ESP_on_grid (UC:450-475, C:453-486).  out: (N,) f32, or (N,4) f16 with
+ * CPET_OUT_CONCAT (each value rounded f64->f32->f16 as the reference's casts do). */
+int cpet_esp_grid(cpet_ctx *ctx, int n_points, const float *x0, unsigned flags, void *out);
+int cpet_esp_grid_dev(cpet_ctx *ctx, int n_points, const float *d_x0, unsigned flags, void *d_out);
+
+/* One streamline step for N independent points: out_i = p_i + h E(p_i)/|E(p_i)|, no zero guard
+ * (propagate_topo, C:489-503; field without softening, C:296-333).  out: (N,3) f32. */
+int cpet_propagate(cpet_ctx *ctx, int n_points, const float *x0, float step_size, float *out);
+int cpet_propagate_dev(cpet_ctx *ctx, int n_points, const float *d_x0, float step_size,
+                       float *d_out);
+
+/* ---------------------------------------------------------------- K2: streamlines ---------- */
+#define CPET_TOPO_CURV_SECOND_DIFF 1u /* curvature from FP32 second differences of positions,
+                                         literally C:575-580.  Default: the algebraically identical
+                                         |e_k x e_k+1| / h from consecutive unit field directions,
+                                         which has no cancellation. */
+
+/* All streamlines of one frame.  Per-line semantics of thread_operation (C:523-591): advance the
+ * seed by p += h E(p)/|E(p)| until n_iter steps or the point is strictly outside +-dims; take two
+ * look-ahead steps at both ends; out[i] = { |seed - end|, (kappa_seed + kappa_end)/2 }.
+ * Replaces the Pool over task_complete_thread (SC:675-712) and the torch path (SC:793-978,
+ * GPU:25-399).  Rows are returned in SEED order.
+ *   seeds (L,3) f32; n_iter (L,) int32; dims (3,) f32 half-widths; out (L,2) f32;
+ *   steps (L,) int32 = steps actually taken per line, may be NULL. */
+int cpet_topo_batch(cpet_ctx *ctx, int n_lines, const float *seeds, const int32_t *n_iter,
+                    float step_size, const float dims[3], unsigned flags, float *out,
+                    int32_t *steps);
+int cpet_topo_batch_dev(cpet_ctx *ctx, int n_lines, const float *d_seeds, const int32_t *d_n_iter,
+                        float step_size, const float dims[3], unsigned flags, float *d_out,
+                        int32_t *d_steps);
+
+/* ---------------------------------------------------------------- K3: histogram / chi^2 ---- */
+/* Batched np.histogram2d (UC:702-707): for each of n_frames frames, counts[f] (nd,nc) int64 of
+ * (dist, curv) pairs with the NumPy rule: edges given explicitly (nd+1 and nc+1 float64, as
+ * np.linspace produces them), bin = searchsorted(edges, v, 'right') - 1, right edge inclusive,
+ * outliers and NaNs dropped.  values: n_frames x n_per_frame rows of 2.
+ *   cpet_hist2d      : host float64 values (what make_histograms parses from .top text)
+ *   cpet_hist2d_f32  : host float32 values (the (L,2) array K2 returns; f32->f64 is exact)
+ *   cpet_hist2d_dev  : device float32 values (K2 output stays on the GPU) */
+int cpet_hist2d(cpet_ctx *ctx, int n_frames, int64_t n_per_frame, const double *values, int nd,
+                const double *d_edges, int nc, const double *c_edges, int64_t *counts);
+int cpet_hist2d_f32(cpet_ctx *ctx, int n_frames, int64_t n_per_frame, const float *values, int nd,
+                    const double *d_edges, int nc, const double *c_edges, int64_t *counts);
+int cpet_hist2d_dev(cpet_ctx *ctx, int n_frames, int64_t n_per_frame, const float *d_values,
+                    int nd, const double *d_edges_host, int nc, const double *c_edges_host,
+                    int64_t *d_counts);
+
+/* Pairwise chi^2 distance matrix (UC:975-978, UC:1003-1015):
+ * out[i][j] = 1/2 sum_{b: h_i[b]+h_j[b] != 0} (h_i[b]-h_j[b])^2 / (h_i[b]+h_j[b]); diagonal 0.
+ * H: (n_hists, n_bins) float64 host; out: (n_hists, n_hists) float64 host. */
+int cpet_chi2_matrix(cpet_ctx *ctx, int n_hists, int64_t n_bins, const double *H, double *out);
+
+/* ---------------------------------------------------------------- measurement -------------- */
+/* Sustained non-tensor FP32 rate of this device from a register-resident FMA loop.
+ * packed=0: FFMA, packed=1: FFMA2 (fma.rn.f32x2).  Returns TFLOP/s in *tflops (2 flop/FMA). */
+int cpet_fp32_peak_probe(cpet_ctx *ctx, int packed, int iters, double *tflops);
+/* Time of the kernels of the last call as measured with CUDA events on the context's stream
+ * (milliseconds; 0 if timing was not enabled with cpet_set_tuning(ctx,"timing",1)). */
+int cpet_last_kernel_ms(cpet_ctx *ctx, double *ms);
+
+/* ================================================================ (A) legacy symbols ======= */
+/* Same names / argument order as the reference's math_module.c so that OPS:8-159 binds them.
+ * All use an implicit process-wide context on device $CPET_B200_DEVICE (default 0), created
+ * lazily on first call (never at load time: the reference forks Pool workers, SC:690).
+ * Hot-path symbols: */
+void compute_looped_field(int total_points, int n_charges, float *x_0, float *x, float *Q,
+                          float *E); /* C:405  OPS:151-159 */
+void compute_batched_field(int total_points, int batch_size, int n_charges, float *x_0, float *x,
+                           float *Q, float *E); /* C:374  OPS:140-149 (no softening) */
+void calc_field(float *E, float *x_init, int n_charges, float *x, float *Q);      /* C:255 OPS:113 */
+void calc_field_base(float *E, float *x_init, int n_charges, float *x, float *Q); /* C:296 OPS:122;
+                                                                       ADDS into E like the reference */
+void calc_esp_base(float *ESP, float *x_init, int n_charges, float *x, float *Q); /* C:453 OPS:131;
+                                                                       ADDS into ESP[0]              */
+void thread_operation(int n_charges, int n_iter, float step_size, float *x_0, float *dimensions,
+                      float *x, float *Q, float *ret); /* C:523  OPS:85-95 */
+/* Helper symbols Math_ops.__init__ sets argtypes on (OPS:26-83); small device kernels. */
+void einsum_ij_i(int rows, int cols, float *A, float *ret);                          /* C:237 */
+void einsum_ij_i_batch(int batch, int rows, int cols, float *A, float *ret);         /* C:214 */
+void einsum_operation(int rows, float *r_mag, float *Q, float *R, float *result);    /* C:181 */
+void einsum_operation_batch(int batch, int rows, float *r_mag, float *Q, float *R,
+                            float *result);                                          /* C:135 */
+void vecaddn(float *ret, float *A, float *B, int lenA);                              /* C:124 */
+void dot(double *ret, double *A, double *B, int rows, int cols);                     /* C:49  */
+void sparse_dot(double *ret, int *indptr, int indptrlen, int *indA, int lenindA, double *A,
+                int lenA, double *B, int size_array);                                /* C:15  */
+/* Development-only dipole tracer of the reference (C:593-660, OPS:97-111): exported so that
+ * Math_ops.__init__ binds; point dipoles mu (n,3). */
+void thread_operation_dipole(int n_dipoles, int n_iter, float step_size, float *x_0,
+                             float *dimensions, float *x, float *mu, float *ret);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPET_B200_H */

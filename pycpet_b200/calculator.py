@@ -1,0 +1,224 @@
+"""Calculator-level entry points of the hot path, same names and return layouts as the reference
+(CPET/utils/calculator.py free functions, CPET/source/calculator.py ``compute_*`` methods), backed
+by libcpetb200.so.  PDB/PQR parsing, atom filtering and the box-frame transform are NOT here: they
+stay in PyCPET's own Python (north_star); these functions start from the arrays that
+``calculator.__init__`` produces (``x``, ``Q``, ``mesh``, ``random_start_points``,
+``random_max_samples``, ``dimensions``, ``step_size``).
+
+Drop-in use with an unmodified PyCPET checkout: ``pycpet_b200.patch_reference()`` (see
+INTEGRATION.md) rebinds ``CPET.utils.calculator.Math`` and the four ``calculator.compute_*``
+methods to the functions below.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .c_ops import Math_ops
+
+_MATH = None
+
+
+def get_math() -> Math_ops:
+    """Process-wide ``Math_ops`` handle (the reference's module-level ``Math``,
+    CPET/utils/calculator.py:29), created on first use so that forked workers never inherit a
+    CUDA context."""
+    global _MATH
+    if _MATH is None:
+        _MATH = Math_ops()
+    return _MATH
+
+
+def __getattr__(name):
+    if name == "Math":
+        return get_math()
+    raise AttributeError(name)
+
+
+# ------------------------------------------------------------------------------------------------
+# free functions (CPET/utils/calculator.py)
+# ------------------------------------------------------------------------------------------------
+def compute_field_on_grid(grid_coords, x, Q):
+    """UC:430-447.  grid_coords (..., 3) -> (N,6) float32 rows [point | E] with the `volume`
+    softening max(r^2, 1e-6); one kernel launch instead of one C loop."""
+    x_0 = np.asarray(grid_coords).reshape(-1, 3)
+    return get_math().field_grid(x_0, x, Q, soften=True, concat=True)
+
+
+def compute_ESP_on_grid(grid_coords, x, Q):
+    """UC:450-475.  -> (N,4) float16 rows [point | ESP]; replaces the Python loop with one
+    ctypes call per grid point."""
+    x_0 = np.asarray(grid_coords).reshape(-1, 3)
+    return get_math().esp_grid(x_0, x, Q, concat_half=True)
+
+
+def calculate_electric_field_c_shared_full_alt(x_0, x, Q):
+    """UC:296-310 -> (3,) float32 field at one point (no softening)."""
+    x_0 = np.asarray(x_0).astype(np.float32)
+    x = np.asarray(x).astype(np.float32)
+    Q = np.asarray(Q).astype(np.float32)
+    return get_math().calc_field(x_0=x_0, x=x, Q=Q)
+
+
+def calculate_esp_c_shared_full(x_0, x, Q):
+    """UC:330-341 -> (1,) float32 potential at one point."""
+    return get_math().calc_esp_base(x_0=x_0, x=x, Q=Q)
+
+
+def calculate_thread_c_shared(x_0, n_iter, x, Q, step_size, dimensions):
+    """UC:344-348 -> (2,) float32 [dist, curv] of one streamline."""
+    return get_math().thread_operation(x_0=x_0, n_iter=n_iter, x=x, Q=Q, step_size=step_size,
+                                       dimensions=dimensions)
+
+
+def propagate_topo(x_0, x, Q, step_size, debug=False):
+    """One normalised-field step p + h E(p)/|E(p)| on the device (the C propagate_topo,
+    math_module.c:489-503; UC:35-54 is its Python twin).  x_0 (3,) or (N,3) -> same shape."""
+    p = np.asarray(x_0, dtype=np.float32)
+    out = get_math().propagate(p.reshape(-1, 3), step_size, x, Q)
+    return out.reshape(p.shape)
+
+
+def compute_topo_batch(seeds, n_iter, x, Q, step_size, dimensions, second_diff=False,
+                       want_steps=False):
+    """The whole-frame call that replaces both Pool.starmap(task_complete_thread, ...)
+    (SC:690-704) and the torch window/filter loop (SC:866-937): (L,2) float32 [dist|curv] in
+    seed order."""
+    return get_math().topo_batch(seeds, n_iter, x, Q, step_size, dimensions,
+                                 second_diff=second_diff, want_steps=want_steps)
+
+
+def distance_numpy(hist1, hist2):
+    """UC:975-978: chi^2 distance between two flattened normalised histograms (device)."""
+    H = np.stack([np.asarray(hist1, dtype=np.float64).ravel(), np.asarray(hist2, dtype=np.float64).ravel()])
+    return float(get_math().chi2_matrix(H)[0, 1])
+
+
+def construct_distance_matrix(histograms):
+    """UC:1003-1015: symmetric pairwise chi^2 matrix with zero diagonal."""
+    return get_math().chi2_matrix(np.asarray(histograms, dtype=np.float64))
+
+
+def histogram2d_counts(values, nd, nc, d_range, c_range):
+    """np.histogram2d(dist, curv, bins=[nd,nc], range=[d_range,c_range]) counts on the device,
+    bit-exact with NumPy.  values: (n,2) or (F,n,2) [dist|curv]."""
+    d_edges = np.linspace(float(d_range[0]), float(d_range[1]), int(nd) + 1)
+    c_edges = np.linspace(float(c_range[0]), float(c_range[1]), int(nc) + 1)
+    return get_math().hist2d(values, d_edges, c_edges)
+
+
+def read_top_file(path):
+    """Parse a .top file (two columns dist, curv; '#' comments) into an (n,2) float64 array."""
+    rows = []
+    with open(path) as fh:
+        for ln in fh:
+            if ln.startswith("#"):
+                continue
+            a = ln.split()
+            if len(a) >= 2:
+                rows.append((float(a[0]), float(a[1])))
+    return np.asarray(rows, dtype=np.float64).reshape(-1, 2)
+
+
+def bin_plan(topologies):
+    """Global ranges and bin counts as make_histograms derives them (UC:640-685): min/max over all
+    frames, bin width 2*IQR/n^(1/3) with n = lines per frame (mean if ragged)."""
+    from scipy.stats import iqr
+    import warnings
+
+    lens = np.array([len(t) for t in topologies])
+    if lens.size and not np.all(lens == lens[0]):
+        warnings.warn(f"Topologies provided are of different sizes, using the mean value of "
+                      f"{np.mean(lens)} to represent binning for {lens}")
+        n_ref = np.mean(lens)
+    else:
+        n_ref = lens[0]
+    dist_all = np.concatenate([np.asarray(t, dtype=np.float64)[:, 0] for t in topologies])
+    curv_all = np.concatenate([np.asarray(t, dtype=np.float64)[:, 1] for t in topologies])
+    d_range = (float(np.min(dist_all)), float(np.max(dist_all)))
+    c_range = (float(np.min(curv_all)), float(np.max(curv_all)))
+    d_res = 2 * iqr(dist_all) / (n_ref ** (1 / 3))
+    c_res = 2 * iqr(curv_all) / (n_ref ** (1 / 3))
+    nd = int((d_range[1] - d_range[0]) / d_res)
+    nc = int((c_range[1] - c_range[0]) / c_res)
+    return d_range, c_range, nd, nc
+
+
+def make_histograms_from_arrays(topologies, plan=None):
+    """Histograms of a list of (n_i,2) [dist|curv] arrays -> (F, nd*nc) float64, each row
+    a/a.sum() flattened row-major (UC:702-713).  Frames of equal length go to the GPU as one
+    batched launch; ragged frames one launch each."""
+    d_range, c_range, nd, nc = plan if plan is not None else bin_plan(topologies)
+    tops = [np.ascontiguousarray(t, dtype=np.float64).reshape(-1, 2) for t in topologies]
+    lens = {len(t) for t in tops}
+    if len(lens) == 1:
+        counts = histogram2d_counts(np.stack(tops), nd, nc, d_range, c_range)
+    else:
+        counts = np.stack([histogram2d_counts(t, nd, nc, d_range, c_range) for t in tops])
+    a = counts.astype(np.float64).reshape(len(tops), -1)
+    return a / a.sum(axis=1, keepdims=True)
+
+
+def make_histograms(topo_files, plot=False):
+    """UC:596-718 with the same signature: list of .top paths -> (F, nd*nc) float64."""
+    return make_histograms_from_arrays([read_top_file(f) for f in topo_files])
+
+
+# ------------------------------------------------------------------------------------------------
+# calculator-level methods (CPET/source/calculator.py); `calc` is any object carrying the
+# attributes the reference's calculator.__init__ sets.
+# ------------------------------------------------------------------------------------------------
+def compute_point_field(calc):
+    """SC:442-463: field at the (already centred) origin -> (3,) float32."""
+    return calculate_electric_field_c_shared_full_alt(np.array([0, 0, 0]), calc.x, calc.Q)
+
+
+def compute_box(calc):
+    """SC:489-507 -> ((N,6) float32 [point|E], mesh.shape)."""
+    return compute_field_on_grid(calc.mesh, calc.x, calc.Q), calc.mesh.shape
+
+
+def compute_box_ESP(calc):
+    """SC:509-528 -> ((N,4) float16 [point|ESP], mesh.shape)."""
+    return compute_ESP_on_grid(calc.mesh, calc.x, calc.Q), calc.mesh.shape
+
+
+def compute_topo_complete_c_shared(calc):
+    """SC:675-712 -> (n_samples,2) [dist|curv] in seed order; also stored as calc.hist."""
+    hist = compute_topo_batch(calc.random_start_points, calc.random_max_samples, calc.x, calc.Q,
+                              calc.step_size, calc.dimensions)
+    try:
+        calc.hist = hist
+    except Exception:
+        pass
+    return hist
+
+
+def compute_topo_GPU_batch_filter(calc):
+    """SC:793-978 -> (n_samples,2) [dist|curv].  The reference returns rows in dump order; this
+    returns seed order (a permutation of the same rows; the reference's own tests sort rows before
+    comparing, tests/test_topology.py:80-95)."""
+    return compute_topo_batch(calc.random_start_points, calc.random_max_samples, calc.x, calc.Q,
+                              calc.step_size, calc.dimensions)
+
+
+def patch_reference():
+    """Rebind an importable, unmodified PyCPET to this backend: the module-level ``Math`` of
+    CPET.utils.calculator plus the hot-path ``compute_*`` methods of the calculator class."""
+    import CPET.utils.calculator as UC      # noqa: N811  (raises ImportError if PyCPET is absent)
+    import CPET.source.calculator as SC     # noqa: N811
+
+    UC.Math = get_math()
+    UC.compute_field_on_grid = compute_field_on_grid
+    UC.compute_ESP_on_grid = compute_ESP_on_grid
+    UC.distance_numpy = distance_numpy
+    UC.construct_distance_matrix = construct_distance_matrix
+    UC.make_histograms = make_histograms
+    SC.compute_field_on_grid = compute_field_on_grid
+    SC.compute_ESP_on_grid = compute_ESP_on_grid
+    cls = SC.calculator
+    cls.compute_box = compute_box
+    cls.compute_box_ESP = compute_box_ESP
+    cls.compute_topo_complete_c_shared = compute_topo_complete_c_shared
+    cls.compute_topo_GPU_batch_filter = compute_topo_GPU_batch_filter
+    cls.compute_point_field = compute_point_field
+    return cls

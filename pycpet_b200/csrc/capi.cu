@@ -1,0 +1,417 @@
+// capi.cu -- the extern "C" boundary of libcpetb200.so (see include/cpet_b200.h).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+#include "cpet_internal.h"
+
+namespace cpet {
+
+static thread_local std::string g_err;
+static thread_local int g_status = 0;
+
+void set_error(int status, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    g_status = status;
+}
+
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return CPET_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 4;            // grow-only with slack
+    want = (want + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(&p, (bytes + 255) & ~(size_t)255);
+        want = (bytes + 255) & ~(size_t)255;
+    }
+    if (e != cudaSuccess) {
+        p = nullptr;
+        set_error(CPET_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return CPET_ERR_CUDA;
+    }
+    cap = want;
+    return CPET_OK;
+}
+
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+KernelTimer::KernelTimer(cpet_ctx* ctx) : c(ctx) {
+    if (c->tune.timing && c->ev0) cudaEventRecord(c->ev0, c->stream);
+}
+KernelTimer::~KernelTimer() {
+    if (c->tune.timing && c->ev1) cudaEventRecord(c->ev1, c->stream);
+}
+
+static int resolve_timer(cpet_ctx* c) {
+    if (!c->tune.timing) { c->last_kernel_ms = 0.0; return CPET_OK; }
+    CPET_CUDA_TRY(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CPET_CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_kernel_ms = ms;
+    return CPET_OK;
+}
+
+static int make_ctx(int device, void* stream, bool borrow, cpet_ctx** out) {
+    CPET_REQUIRE(out != nullptr, CPET_ERR_INVALID, "cpet_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error(CPET_ERR_NO_DEVICE, "no CUDA device available (%s); libcpetb200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return CPET_ERR_NO_DEVICE;
+    }
+    CPET_REQUIRE(device >= 0 && device < n, CPET_ERR_INVALID, "device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    CPET_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(CPET_ERR_NO_DEVICE,
+                  "device %d (%s) is compute capability %d.%d; this library carries sm_100a code only",
+                  device, prop.name, prop.major, prop.minor);
+        return CPET_ERR_NO_DEVICE;
+    }
+    CPET_CUDA_TRY(cudaSetDevice(device));
+    cpet_ctx* c = new cpet_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (borrow) {
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    } else {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete c;
+            set_error(CPET_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+            return CPET_ERR_CUDA;
+        }
+        c->own_stream = true;
+    }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    *out = c;
+    return CPET_OK;
+}
+
+#define CTX_GUARD(c)                                                                     \
+    CPET_REQUIRE((c) != nullptr, CPET_ERR_INVALID, "context is NULL");                   \
+    CPET_CUDA_TRY(cudaSetDevice((c)->device))
+
+static int resolve_topo_counters(cpet_ctx* c) {
+    if (c->last_counters[1] >= 0) return CPET_OK;
+    unsigned long long ev = 0;
+    CPET_CUDA_TRY(cudaMemcpyAsync(&ev, c->counters.as<unsigned char>() + 8, sizeof(ev),
+                                  cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->last_counters[2] = (int64_t)ev;
+    c->last_counters[1] = (int64_t)ev * (int64_t)c->n_charges;
+    return CPET_OK;
+}
+
+}  // namespace cpet
+
+using namespace cpet;
+
+extern "C" {
+
+int cpet_abi_version(void) { return CPET_ABI_VERSION; }
+const char* cpet_last_error(void) { return g_err.c_str(); }
+int cpet_last_status(void) { return g_status; }
+void cpet_clear_error(void) { g_err.clear(); g_status = 0; }
+
+int cpet_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int cpet_create(int device, cpet_ctx** out) { return make_ctx(device, nullptr, false, out); }
+int cpet_create_on_stream(int device, void* cuda_stream, cpet_ctx** out) {
+    return make_ctx(device, cuda_stream, true, out);
+}
+
+int cpet_destroy(cpet_ctx* c) {
+    if (!c) return CPET_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->charges.release(); c->raw_x.release(); c->raw_q.release();
+    c->in0.release(); c->in1.release(); c->out0.release(); c->out1.release();
+    c->work0.release(); c->work1.release(); c->work2.release(); c->counters.release();
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return CPET_OK;
+}
+
+int cpet_sync(cpet_ctx* c) {
+    CTX_GUARD(c);
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPET_OK;
+}
+
+int cpet_device_of(cpet_ctx* c) { return c ? c->device : -1; }
+
+int cpet_set_tuning(cpet_ctx* c, const char* key, int value) {
+    CPET_REQUIRE(c && key, CPET_ERR_INVALID, "cpet_set_tuning: NULL argument");
+    Tuning& t = c->tune;
+    struct { const char* k; int* v; } tab[] = {
+        {"k1_threads", &t.k1_threads}, {"k1_points", &t.k1_points}, {"k1_lanes", &t.k1_lanes},
+        {"k1_tile_pairs", &t.k1_tile_pairs}, {"k1_stages", &t.k1_stages}, {"k1_splits", &t.k1_splits},
+        {"k2_threads", &t.k2_threads}, {"k2_lanes", &t.k2_lanes}, {"k2_tile_pairs", &t.k2_tile_pairs},
+        {"k2_stages", &t.k2_stages}, {"k2_ctas_per_sm", &t.k2_ctas_per_sm}, {"k2_sort", &t.k2_sort},
+        {"timing", &t.timing},
+    };
+    for (auto& e : tab) {
+        if (strcmp(e.k, key) == 0) {
+            if (e.v == &t.k2_sort) *e.v = value;
+            else *e.v = value > 0 ? value : 0;
+            return CPET_OK;
+        }
+    }
+    set_error(CPET_ERR_INVALID, "unknown tuning key '%s'", key);
+    return CPET_ERR_INVALID;
+}
+
+int cpet_last_counters(cpet_ctx* c, int64_t out[3]) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(out != nullptr, CPET_ERR_INVALID, "out is NULL");
+    if (int rc = resolve_topo_counters(c)) return rc;
+    out[0] = c->last_counters[0]; out[1] = c->last_counters[1]; out[2] = c->last_counters[2];
+    return CPET_OK;
+}
+
+int cpet_last_kernel_ms(cpet_ctx* c, double* ms) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(ms != nullptr, CPET_ERR_INVALID, "ms is NULL");
+    if (int rc = resolve_timer(c)) return rc;
+    *ms = c->last_kernel_ms;
+    return CPET_OK;
+}
+
+// ---------------------------------------------------------------- charges -------------------
+int cpet_set_charges_dev(cpet_ctx* c, int n_charges, const float* d_x, const float* d_Q) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_charges >= 0, CPET_ERR_INVALID, "n_charges < 0");
+    CPET_REQUIRE(n_charges == 0 || (d_x && d_Q), CPET_ERR_INVALID, "NULL charge arrays");
+    return launch_pack_charges(c, n_charges, d_x, d_Q);
+}
+
+int cpet_set_charges(cpet_ctx* c, int n_charges, const float* x, const float* Q) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_charges >= 0, CPET_ERR_INVALID, "n_charges < 0");
+    CPET_REQUIRE(n_charges == 0 || (x && Q), CPET_ERR_INVALID, "NULL charge arrays");
+    const size_t m = (size_t)(n_charges > 0 ? n_charges : 1);
+    if (int rc = c->raw_x.reserve(sizeof(float) * 3 * m)) return rc;
+    if (int rc = c->raw_q.reserve(sizeof(float) * m)) return rc;
+    if (n_charges > 0) {
+        CPET_CUDA_TRY(cudaMemcpyAsync(c->raw_x.p, x, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, c->stream));
+        CPET_CUDA_TRY(cudaMemcpyAsync(c->raw_q.p, Q, sizeof(float) * m, cudaMemcpyHostToDevice, c->stream));
+    }
+    return launch_pack_charges(c, n_charges, c->raw_x.as<float>(), c->raw_q.as<float>());
+}
+
+// ---------------------------------------------------------------- K1 -------------------------
+static int field_mode_of(unsigned flags) { return (flags & CPET_FIELD_SOFTEN) ? MODE_FIELD_SOFT : MODE_FIELD_RAW; }
+
+int cpet_field_grid_dev(cpet_ctx* c, int n_points, const float* d_x0, unsigned flags, float* d_out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_points >= 0, CPET_ERR_INVALID, "n_points < 0");
+    CPET_REQUIRE((flags & ~(CPET_FIELD_SOFTEN | CPET_OUT_CONCAT)) == 0, CPET_ERR_INVALID, "unknown flag bits 0x%x", flags);
+    CPET_REQUIRE(n_points == 0 || (d_x0 && d_out), CPET_ERR_INVALID, "NULL point/output arrays");
+    return launch_field_grid(c, field_mode_of(flags), n_points, d_x0, (flags & CPET_OUT_CONCAT) ? 1 : 0, d_out);
+}
+
+int cpet_field_grid(cpet_ctx* c, int n_points, const float* x0, unsigned flags, float* out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_points >= 0, CPET_ERR_INVALID, "n_points < 0");
+    CPET_REQUIRE(n_points == 0 || (x0 && out), CPET_ERR_INVALID, "NULL point/output arrays");
+    if (n_points == 0) return CPET_OK;
+    const size_t n = (size_t)n_points;
+    const size_t out_floats = (flags & CPET_OUT_CONCAT) ? 6 * n : 3 * n;
+    if (int rc = c->in0.reserve(sizeof(float) * 3 * n)) return rc;
+    if (int rc = c->out0.reserve(sizeof(float) * out_floats)) return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, x0, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = cpet_field_grid_dev(c, n_points, c->in0.as<float>(), flags, c->out0.as<float>())) return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, sizeof(float) * out_floats, cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPET_OK;
+}
+
+int cpet_esp_grid_dev(cpet_ctx* c, int n_points, const float* d_x0, unsigned flags, void* d_out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_points >= 0, CPET_ERR_INVALID, "n_points < 0");
+    CPET_REQUIRE((flags & ~CPET_OUT_CONCAT) == 0, CPET_ERR_INVALID, "unknown flag bits 0x%x", flags);
+    CPET_REQUIRE(n_points == 0 || (d_x0 && d_out), CPET_ERR_INVALID, "NULL point/output arrays");
+    return launch_field_grid(c, MODE_ESP, n_points, d_x0, (flags & CPET_OUT_CONCAT) ? 3 : 2, d_out);
+}
+
+int cpet_esp_grid(cpet_ctx* c, int n_points, const float* x0, unsigned flags, void* out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_points >= 0, CPET_ERR_INVALID, "n_points < 0");
+    CPET_REQUIRE(n_points == 0 || (x0 && out), CPET_ERR_INVALID, "NULL point/output arrays");
+    if (n_points == 0) return CPET_OK;
+    const size_t n = (size_t)n_points;
+    const size_t out_bytes = (flags & CPET_OUT_CONCAT) ? 8 * n : 4 * n;
+    if (int rc = c->in0.reserve(sizeof(float) * 3 * n)) return rc;
+    if (int rc = c->out0.reserve(out_bytes)) return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, x0, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = cpet_esp_grid_dev(c, n_points, c->in0.as<float>(), flags, c->out0.p)) return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPET_OK;
+}
+
+int cpet_propagate_dev(cpet_ctx* c, int n_points, const float* d_x0, float step_size, float* d_out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_points >= 0, CPET_ERR_INVALID, "n_points < 0");
+    CPET_REQUIRE(n_points == 0 || (d_x0 && d_out), CPET_ERR_INVALID, "NULL point/output arrays");
+    return launch_field_grid(c, MODE_FIELD_RAW, n_points, d_x0, 4, d_out, step_size);
+}
+
+int cpet_propagate(cpet_ctx* c, int n_points, const float* x0, float step_size, float* out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_points >= 0, CPET_ERR_INVALID, "n_points < 0");
+    CPET_REQUIRE(n_points == 0 || (x0 && out), CPET_ERR_INVALID, "NULL point/output arrays");
+    if (n_points == 0) return CPET_OK;
+    const size_t n = (size_t)n_points;
+    if (int rc = c->in0.reserve(sizeof(float) * 3 * n)) return rc;
+    if (int rc = c->out0.reserve(sizeof(float) * 3 * n)) return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, x0, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = cpet_propagate_dev(c, n_points, c->in0.as<float>(), step_size, c->out0.as<float>())) return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPET_OK;
+}
+
+// ---------------------------------------------------------------- K2 -------------------------
+int cpet_topo_batch_dev(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d_n_iter,
+                        float step_size, const float dims[3], unsigned flags, float* d_out,
+                        int32_t* d_steps) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_lines >= 0, CPET_ERR_INVALID, "n_lines < 0");
+    CPET_REQUIRE((flags & ~CPET_TOPO_CURV_SECOND_DIFF) == 0, CPET_ERR_INVALID, "unknown flag bits 0x%x", flags);
+    CPET_REQUIRE(dims != nullptr, CPET_ERR_INVALID, "dims is NULL");
+    CPET_REQUIRE(n_lines == 0 || (d_seeds && d_n_iter && d_out), CPET_ERR_INVALID, "NULL seed/n_iter/output arrays");
+    return launch_topo(c, n_lines, d_seeds, d_n_iter, step_size, dims, flags, d_out, d_steps);
+}
+
+int cpet_topo_batch(cpet_ctx* c, int n_lines, const float* seeds, const int32_t* n_iter,
+                    float step_size, const float dims[3], unsigned flags, float* out,
+                    int32_t* steps) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_lines >= 0, CPET_ERR_INVALID, "n_lines < 0");
+    CPET_REQUIRE(n_lines == 0 || (seeds && n_iter && out), CPET_ERR_INVALID, "NULL seed/n_iter/output arrays");
+    if (n_lines == 0) return CPET_OK;
+    const size_t n = (size_t)n_lines;
+    if (int rc = c->in0.reserve(sizeof(float) * 3 * n)) return rc;
+    if (int rc = c->in1.reserve(sizeof(int32_t) * n)) return rc;
+    if (int rc = c->out0.reserve(sizeof(float) * 2 * n)) return rc;
+    if (steps) { if (int rc = c->out1.reserve(sizeof(int32_t) * n)) return rc; }
+    CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, seeds, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    CPET_CUDA_TRY(cudaMemcpyAsync(c->in1.p, n_iter, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = cpet_topo_batch_dev(c, n_lines, c->in0.as<float>(), c->in1.as<int32_t>(), step_size, dims,
+                                     flags, c->out0.as<float>(), steps ? c->out1.as<int32_t>() : nullptr))
+        return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (steps)
+        CPET_CUDA_TRY(cudaMemcpyAsync(steps, c->out1.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPET_OK;
+}
+
+// ---------------------------------------------------------------- K3 -------------------------
+static int upload_edges(cpet_ctx* c, int nd, const double* d_edges, int nc, const double* c_edges,
+                        const double** dev_d, const double** dev_c) {
+    CPET_REQUIRE(nd >= 1 && nc >= 1, CPET_ERR_INVALID, "histogram needs nd >= 1 and nc >= 1");
+    CPET_REQUIRE(d_edges && c_edges, CPET_ERR_INVALID, "NULL edge arrays");
+    const size_t n = (size_t)nd + nc + 2;
+    if (int rc = c->work2.reserve(sizeof(double) * n)) return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(c->work2.p, d_edges, sizeof(double) * (nd + 1), cudaMemcpyHostToDevice, c->stream));
+    CPET_CUDA_TRY(cudaMemcpyAsync(c->work2.as<double>() + nd + 1, c_edges, sizeof(double) * (nc + 1),
+                                  cudaMemcpyHostToDevice, c->stream));
+    *dev_d = c->work2.as<double>();
+    *dev_c = c->work2.as<double>() + nd + 1;
+    return CPET_OK;
+}
+
+int cpet_hist2d_dev(cpet_ctx* c, int n_frames, int64_t n_per_frame, const float* d_values, int nd,
+                    const double* d_edges_host, int nc, const double* c_edges_host, int64_t* d_counts) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_frames >= 0 && n_per_frame >= 0, CPET_ERR_INVALID, "negative sizes");
+    CPET_REQUIRE(d_counts != nullptr, CPET_ERR_INVALID, "counts is NULL");
+    const double *dd, *dc;
+    if (int rc = upload_edges(c, nd, d_edges_host, nc, c_edges_host, &dd, &dc)) return rc;
+    return launch_hist2d(c, n_frames, n_per_frame, d_values, false, nd, dd, nc, dc,
+                         reinterpret_cast<unsigned long long*>(d_counts));
+}
+
+static int hist2d_host(cpet_ctx* c, int n_frames, int64_t n_per_frame, const void* values, bool f64,
+                       int nd, const double* d_edges, int nc, const double* c_edges, int64_t* counts) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_frames >= 0 && n_per_frame >= 0, CPET_ERR_INVALID, "negative sizes");
+    CPET_REQUIRE(counts != nullptr, CPET_ERR_INVALID, "counts is NULL");
+    CPET_REQUIRE((int64_t)n_frames * n_per_frame == 0 || values, CPET_ERR_INVALID, "values is NULL");
+    const double *dd, *dc;
+    if (int rc = upload_edges(c, nd, d_edges, nc, c_edges, &dd, &dc)) return rc;
+    const size_t nval = (size_t)n_frames * (size_t)n_per_frame * 2;
+    const size_t vbytes = nval * (f64 ? sizeof(double) : sizeof(float));
+    const size_t cbytes = sizeof(int64_t) * (size_t)n_frames * nd * nc;
+    if (int rc = c->in0.reserve(vbytes ? vbytes : 8)) return rc;
+    if (int rc = c->out0.reserve(cbytes ? cbytes : 8)) return rc;
+    if (vbytes) CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, values, vbytes, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = launch_hist2d(c, n_frames, n_per_frame, c->in0.p, f64, nd, dd, nc, dc,
+                               c->out0.as<unsigned long long>()))
+        return rc;
+    if (cbytes) CPET_CUDA_TRY(cudaMemcpyAsync(counts, c->out0.p, cbytes, cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPET_OK;
+}
+
+int cpet_hist2d(cpet_ctx* c, int n_frames, int64_t n_per_frame, const double* values, int nd,
+                const double* d_edges, int nc, const double* c_edges, int64_t* counts) {
+    return hist2d_host(c, n_frames, n_per_frame, values, true, nd, d_edges, nc, c_edges, counts);
+}
+
+int cpet_hist2d_f32(cpet_ctx* c, int n_frames, int64_t n_per_frame, const float* values, int nd,
+                    const double* d_edges, int nc, const double* c_edges, int64_t* counts) {
+    return hist2d_host(c, n_frames, n_per_frame, values, false, nd, d_edges, nc, c_edges, counts);
+}
+
+int cpet_chi2_matrix(cpet_ctx* c, int n_hists, int64_t n_bins, const double* H, double* out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_hists >= 0 && n_bins >= 0, CPET_ERR_INVALID, "negative sizes");
+    if (n_hists == 0) return CPET_OK;
+    CPET_REQUIRE(H && out, CPET_ERR_INVALID, "NULL arrays");
+    const size_t hb = sizeof(double) * (size_t)n_hists * (size_t)n_bins;
+    const size_t ob = sizeof(double) * (size_t)n_hists * n_hists;
+    if (int rc = c->in0.reserve(hb ? hb : 8)) return rc;
+    if (int rc = c->out0.reserve(ob)) return rc;
+    if (hb) CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, H, hb, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = launch_chi2(c, n_hists, n_bins, c->in0.as<double>(), c->out0.as<double>())) return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, ob, cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPET_OK;
+}
+
+int cpet_fp32_peak_probe(cpet_ctx* c, int packed, int iters, double* tflops) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(tflops != nullptr, CPET_ERR_INVALID, "tflops is NULL");
+    return launch_fp32_probe(c, packed, iters, tflops);
+}
+
+}  // extern "C"

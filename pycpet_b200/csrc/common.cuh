@@ -1,0 +1,194 @@
+// common.cuh -- device-side building blocks shared by the sm_100a kernels.
+//
+//  * packed FP32x2 arithmetic (Blackwell FADD2/FMUL2/FFMA2): two point-charge pairs per
+//    instruction, so the FP32 pipe is fed with half the issue slots;
+//  * mbarrier + 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) used to stage charge tiles;
+//  * the pair-evaluation inner loops for the three flavours of the Coulomb sum.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cpet {
+
+typedef unsigned long long u64;
+
+// Coulomb factor and softening exactly as the reference stores them in `float`
+// (CPET/utils/math_module.c:412 and :407).
+#define CPET_COULOMB_K 14.3996451f
+#define CPET_SOFT_EPS 1e-6f
+
+// One charge pair (charges 2j and 2j+1) = 32 bytes = two 16-byte shared-memory vectors:
+//   a = { (-x0,-x1), (-y0,-y1) }    b = { (-z0,-z1), (q0,q1) }
+// Coordinates are stored negated so that d = p + (-x) is a single packed add.
+struct __align__(16) PairA { u64 nx, ny; };
+struct __align__(16) PairB { u64 nz, q; };
+struct __align__(32) ChargePair { PairA a; PairB b; };
+static_assert(sizeof(ChargePair) == 32, "charge pair must be 32 bytes");
+
+// A padding charge: q = 0 at a far but finite position (no inf*0 in the raw-field mode).
+#define CPET_PAD_COORD 1.0e8f
+
+enum FieldMode : int { MODE_FIELD_SOFT = 0, MODE_FIELD_RAW = 1, MODE_ESP = 2 };
+
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier + TMA 1-D bulk copy
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion signalled on `bar` (bytes multiple of 16, both
+// addresses 16-byte aligned).
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Pair evaluation.  P evaluation points per thread (coordinates duplicated into both halves
+// of a packed register), charge pairs read as broadcast LDS.128.  Accumulators are packed
+// {even-charge sum, odd-charge sum}.
+// ------------------------------------------------------------------------------------------
+template <int P>
+struct PointRegs {
+    u64 px[P], py[P], pz[P];      // {p,p}
+    u64 ax[P], ay[P], az[P];      // FP32 partial sums for the current tile (az unused for ESP)
+};
+
+template <int MODE, int P>
+__device__ __forceinline__ void eval_pair(const PairA a, const PairB b, PointRegs<P>& r) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const u64 dx = add2(r.px[p], a.nx);
+        const u64 dy = add2(r.py[p], a.ny);
+        const u64 dz = add2(r.pz[p], b.nz);
+        u64 r2 = mul2(dx, dx);
+        r2 = fma2(dy, dy, r2);
+        r2 = fma2(dz, dz, r2);
+        float r2a, r2b;
+        upk2(r2, r2a, r2b);
+        if (MODE == MODE_FIELD_SOFT) {
+            r2a = fmaxf(r2a, CPET_SOFT_EPS);
+            r2b = fmaxf(r2b, CPET_SOFT_EPS);
+        }
+        const u64 inv = pk2(rsqrt_approx(r2a), rsqrt_approx(r2b));
+        if (MODE == MODE_ESP) {
+            r.ax[p] = fma2(inv, b.q, r.ax[p]);
+        } else {
+            const u64 t = mul2(inv, inv);
+            const u64 u = mul2(inv, b.q);
+            const u64 s = mul2(t, u);
+            r.ax[p] = fma2(s, dx, r.ax[p]);
+            r.ay[p] = fma2(s, dy, r.ay[p]);
+            r.az[p] = fma2(s, dz, r.az[p]);
+        }
+    }
+}
+
+// Accumulate pairs [first, n) with stride `stride` of one shared-memory tile.
+template <int MODE, int P, int UNROLL>
+__device__ __forceinline__ void eval_tile(const ChargePair* __restrict__ tile, int first, int n,
+                                          int stride, PointRegs<P>& r) {
+#pragma unroll UNROLL
+    for (int j = first; j < n; j += stride) {
+        const PairA a = tile[j].a;
+        const PairB b = tile[j].b;
+        eval_pair<MODE, P>(a, b, r);
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void clear_partials(PointRegs<P>& r) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) r.ax[p] = r.ay[p] = r.az[p] = 0ull;
+}
+
+// FP32 tile partials -> FP64 running sums (3 doubles per point; ESP uses [0] only).
+template <int MODE, int P>
+__device__ __forceinline__ void flush_partials(PointRegs<P>& r, double (&acc)[P][3]) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        float lo, hi;
+        upk2(r.ax[p], lo, hi);
+        acc[p][0] += (double)lo + (double)hi;
+        if (MODE != MODE_ESP) {
+            upk2(r.ay[p], lo, hi);
+            acc[p][1] += (double)lo + (double)hi;
+            upk2(r.az[p], lo, hi);
+            acc[p][2] += (double)lo + (double)hi;
+        }
+    }
+    clear_partials<P>(r);
+}
+
+template <int P>
+__device__ __forceinline__ void set_point(PointRegs<P>& r, int p, float x, float y, float z) {
+    r.px[p] = pk2(x, x);
+    r.py[p] = pk2(y, y);
+    r.pz[p] = pk2(z, z);
+}
+
+__device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, lane_mask);
+    hi = __shfl_xor_sync(0xffffffffu, hi, lane_mask);
+    return __hiloint2double(hi, lo);
+}
+
+}  // namespace cpet

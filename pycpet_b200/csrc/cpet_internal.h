@@ -1,0 +1,101 @@
+// cpet_internal.h -- host-side internals of libcpetb200.so (context, scratch, launchers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/cpet_b200.h"
+#include "common.cuh"
+
+namespace cpet {
+
+void set_error(int status, const char* fmt, ...);
+
+#define CPET_CUDA_TRY(expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            cpet::set_error(CPET_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                   \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+            return CPET_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define CPET_REQUIRE(cond, status, ...)                                                      \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            cpet::set_error(status, __VA_ARGS__);                                            \
+            return status;                                                                   \
+        }                                                                                    \
+    } while (0)
+
+// Grow-only device buffer.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Tuning {
+    int k1_threads = 0, k1_points = 0, k1_lanes = 0, k1_tile_pairs = 0, k1_stages = 0;
+    int k1_splits = 0;
+    int k2_threads = 0, k2_lanes = 0, k2_tile_pairs = 0, k2_stages = 0, k2_ctas_per_sm = 0;
+    int k2_sort = -1;   // -1 heuristic (on), 0 off, 1 on
+    int timing = 0;
+};
+
+}  // namespace cpet
+
+struct cpet_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // current frame
+    int n_charges = 0;
+    int n_pairs = 0;                 // padded
+    cpet::DevBuf charges;            // ChargePair[n_pairs]
+    cpet::DevBuf raw_x, raw_q;       // staging for host uploads
+    // scratch
+    cpet::DevBuf in0, in1, out0, out1, work0, work1, work2, counters;
+    cpet::Tuning tune;
+    int64_t last_counters[3] = {0, 0, 0};
+    double last_kernel_ms = 0.0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace cpet {
+
+// ---- launchers implemented in the .cu files (all enqueue on ctx->stream, never sync) --------
+int launch_pack_charges(cpet_ctx* c, int n_charges, const float* d_x, const float* d_q);
+
+// K1.  out_kind: 0 = (N,3) f32, 1 = (N,6) f32 [x0|E], 2 = (N,) f32 phi, 3 = (N,4) f16 [x0|phi],
+//                4 = (N,3) f32 p + step*E/|E|
+int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, int out_kind,
+                      void* d_out, float step = 0.0f);
+
+// K2
+int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d_n_iter,
+                float step, const float dims[3], unsigned flags, float* d_out, int32_t* d_steps);
+
+// K3
+int launch_hist2d(cpet_ctx* c, int n_frames, int64_t n_per_frame, const void* d_values,
+                  bool values_f64, int nd, const double* d_edges_dev, int nc,
+                  const double* c_edges_dev, unsigned long long* d_counts);
+int launch_chi2(cpet_ctx* c, int n_hists, int64_t n_bins, const double* d_H, double* d_out);
+
+// misc
+int launch_fp32_probe(cpet_ctx* c, int packed, int iters, double* tflops);
+
+struct KernelTimer {
+    cpet_ctx* c;
+    explicit KernelTimer(cpet_ctx* ctx);
+    ~KernelTimer();
+};
+
+}  // namespace cpet

@@ -1,0 +1,402 @@
+// field.cu -- K1: Coulomb E-field / potential of M point charges on N points (sm_100a).
+//
+// Replaces compute_looped_field (CPET/utils/math_module.c:405-451), the per-point loops over
+// calc_field / calc_field_base (C:255-333) and calc_esp_base (C:453-486; loop at
+// CPET/utils/calculator.py:468-469).
+//
+// Shape of the kernel (N-body style, no tensor cores):
+//   * charges are pre-packed in HBM as 32-byte pairs (common.cuh: ChargePair); a CTA streams its
+//     charge range through a ring of shared-memory tiles filled by 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx), so loads of tile t+S-1 overlap the math on tile t;
+//   * every thread keeps P points (G=1) in registers, or G lanes share one point and split the
+//     pairs of each tile (small N); each broadcast LDS.128 pair feeds 2*P pair evaluations of
+//     packed FADD2/FMUL2/FFMA2 + MUFU.RSQ;
+//   * FP32 accumulation inside a tile (even/odd charge sums), FP64 across tiles;
+//   * for small N the charge range is additionally split over gridDim.y and a finalize kernel
+//     sums the FP64 partials, so that >= 2 CTAs/SM are in flight even for a 11^3 grid.
+#include "cpet_internal.h"
+#include <cuda_fp16.h>
+
+namespace cpet {
+
+// ---------------------------------------------------------------------------------------------
+// charge packing: (M,3) f32 + (M,) f32  ->  ChargePair[ceil(M/2)]
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_charges_kernel(const float* __restrict__ x, const float* __restrict__ q,
+                                    int n_charges, int n_pairs, ChargePair* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_pairs) return;
+    float cx[2], cy[2], cz[2], cq[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = 2 * j + h;
+        if (i < n_charges) {
+            cx[h] = -x[3 * (size_t)i + 0];
+            cy[h] = -x[3 * (size_t)i + 1];
+            cz[h] = -x[3 * (size_t)i + 2];
+            cq[h] = q[i];
+        } else {
+            cx[h] = cy[h] = cz[h] = -CPET_PAD_COORD;
+            cq[h] = 0.0f;
+        }
+    }
+    ChargePair cp;
+    cp.a.nx = pk2(cx[0], cx[1]);
+    cp.a.ny = pk2(cy[0], cy[1]);
+    cp.b.nz = pk2(cz[0], cz[1]);
+    cp.b.q = pk2(cq[0], cq[1]);
+    out[j] = cp;
+}
+
+int launch_pack_charges(cpet_ctx* c, int n_charges, const float* d_x, const float* d_q) {
+    const int n_pairs = (n_charges + 1) / 2;
+    if (int rc = c->charges.reserve(sizeof(ChargePair) * (size_t)(n_pairs > 0 ? n_pairs : 1))) return rc;
+    c->n_charges = n_charges;
+    c->n_pairs = n_pairs;
+    if (n_pairs > 0) {
+        pack_charges_kernel<<<(n_pairs + 255) / 256, 256, 0, c->stream>>>(
+            d_x, d_q, n_charges, n_pairs, c->charges.as<ChargePair>());
+        CPET_CUDA_TRY(cudaGetLastError());
+    }
+    return CPET_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------------------
+struct K1Params {
+    const ChargePair* charges;
+    int n_pairs;
+    int pairs_per_split;
+    int tile_pairs;
+    int stages;
+    const float* x0;
+    int n_points;
+    int out_kind;     // 0 (N,3) f32 | 1 (N,6) f32 [x0|E] | 2 (N,) f32 | 3 (N,4) f16 [x0|phi]
+                      // 4 (N,3) f32 p + h E/|E|  (propagate_topo, C:489-503)
+    float step;
+    void* out;
+    double* partial;  // [splits][n_points][3] when gridDim.y > 1
+};
+
+__device__ __forceinline__ void store_result(int out_kind, float step, void* out, int pt, float x,
+                                             float y, float z, double s0, double s1, double s2) {
+    const double k = (double)CPET_COULOMB_K;
+    if (out_kind == 0) {
+        float* o = (float*)out + 3 * (size_t)pt;
+        o[0] = (float)(k * s0); o[1] = (float)(k * s1); o[2] = (float)(k * s2);
+    } else if (out_kind == 1) {
+        float2* o = (float2*)((float*)out + 6 * (size_t)pt);
+        o[0] = make_float2(x, y);
+        o[1] = make_float2(z, (float)(k * s0));
+        o[2] = make_float2((float)(k * s1), (float)(k * s2));
+    } else if (out_kind == 2) {
+        ((float*)out)[pt] = (float)(k * s0);
+    } else if (out_kind == 4) {
+        // no zero guard, as in the reference: E = 0 -> NaN
+        const double inv_n = 1.0 / sqrt(s0 * s0 + s1 * s1 + s2 * s2);
+        float* o = (float*)out + 3 * (size_t)pt;
+        o[0] = (float)((double)x + (double)step * s0 * inv_n);
+        o[1] = (float)((double)y + (double)step * s1 * inv_n);
+        o[2] = (float)((double)z + (double)step * s2 * inv_n);
+    } else {
+        // float64 -> float32 -> float16, the two casts the reference applies (UC:464-475)
+        __half2 lo = __floats2half2_rn(x, y);
+        __half2 hi = __floats2half2_rn(z, (float)(k * s0));
+        uint2 v;
+        v.x = *reinterpret_cast<unsigned*>(&lo);
+        v.y = *reinterpret_cast<unsigned*>(&hi);
+        ((uint2*)out)[pt] = v;
+    }
+}
+
+template <int MODE, int P, int G>
+__global__ void __launch_bounds__(256) k1_grid_kernel(const K1Params prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    ChargePair* ring = reinterpret_cast<ChargePair*>(smem_raw + 128);
+
+    const int tid = threadIdx.x;
+    const int lane_g = tid % G;
+    const int groups = blockDim.x / G;
+    const int grp = tid / G;
+    const int S = prm.stages;
+    const int TP = prm.tile_pairs;
+
+    const int pbeg = blockIdx.y * prm.pairs_per_split;
+    const int pend = min(prm.n_pairs, pbeg + prm.pairs_per_split);
+    const int npairs = max(0, pend - pbeg);
+    const int ntiles = (npairs + TP - 1) / TP;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int t) {
+        const int stage = t % S;
+        const int n_t = min(TP, npairs - t * TP);
+        const uint32_t bytes = (uint32_t)n_t * (uint32_t)sizeof(ChargePair);
+        mbar_expect_tx(&full[stage], bytes);
+        tma_load_1d(ring + (size_t)stage * TP, prm.charges + pbeg + (size_t)t * TP, bytes,
+                    &full[stage]);
+    };
+    if (tid == 0) {
+        const int pre = min(S, ntiles);
+        for (int t = 0; t < pre; ++t) issue(t);
+    }
+
+    PointRegs<P> r;
+    float px[P], py[P], pz[P];
+    int pt[P];
+    double acc[P][3];
+    const int base = blockIdx.x * groups * P;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        pt[p] = base + p * groups + grp;
+        const int ld = min(pt[p], prm.n_points - 1);
+        px[p] = prm.x0[3 * (size_t)ld + 0];
+        py[p] = prm.x0[3 * (size_t)ld + 1];
+        pz[p] = prm.x0[3 * (size_t)ld + 2];
+        set_point<P>(r, p, px[p], py[p], pz[p]);
+        acc[p][0] = acc[p][1] = acc[p][2] = 0.0;
+    }
+    clear_partials<P>(r);
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int stage = t % S;
+        mbar_wait(&full[stage], (uint32_t)((t / S) & 1));
+        const int n_t = min(TP, npairs - t * TP);
+        eval_tile<MODE, P, (P >= 4 ? 2 : 4)>(ring + (size_t)stage * TP, lane_g, n_t, G, r);
+        flush_partials<MODE, P>(r, acc);
+        if (t + S < ntiles) {
+            __syncthreads();           // every warp is done reading this stage
+            if (tid == 0) issue(t + S);
+        }
+    }
+
+    if (G > 1) {
+#pragma unroll
+        for (int m = G / 2; m >= 1; m >>= 1) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                acc[p][0] += shfl_xor_f64(acc[p][0], m);
+                if (MODE != MODE_ESP) {
+                    acc[p][1] += shfl_xor_f64(acc[p][1], m);
+                    acc[p][2] += shfl_xor_f64(acc[p][2], m);
+                }
+            }
+        }
+    }
+    if (lane_g != 0) return;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        if (pt[p] >= prm.n_points) continue;
+        if (gridDim.y == 1) {
+            store_result(prm.out_kind, prm.step, prm.out, pt[p], px[p], py[p], pz[p], acc[p][0],
+                         acc[p][1], acc[p][2]);
+        } else {
+            double* o = prm.partial + ((size_t)blockIdx.y * prm.n_points + pt[p]) * 3;
+            o[0] = acc[p][0]; o[1] = acc[p][1]; o[2] = acc[p][2];
+        }
+    }
+}
+
+__global__ void k1_finalize_kernel(const double* __restrict__ partial, int splits, int n_points,
+                                   const float* __restrict__ x0, int out_kind, float step,
+                                   void* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_points) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int s = 0; s < splits; ++s) {
+        const double* p = partial + ((size_t)s * n_points + i) * 3;
+        s0 += p[0]; s1 += p[1]; s2 += p[2];
+    }
+    store_result(out_kind, step, out, i, x0[3 * (size_t)i], x0[3 * (size_t)i + 1], x0[3 * (size_t)i + 2],
+                 s0, s1, s2);
+}
+
+template <int MODE, int P, int G>
+static int launch_k1_inst(cpet_ctx* c, const K1Params& prm, dim3 grid, int threads, size_t smem) {
+    auto kern = k1_grid_kernel<MODE, P, G>;
+    CPET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, c->stream>>>(prm);
+    CPET_CUDA_TRY(cudaGetLastError());
+    return CPET_OK;
+}
+
+template <int MODE>
+static int launch_k1_mode(cpet_ctx* c, const K1Params& prm, int P, int G, dim3 grid, int threads,
+                          size_t smem) {
+    if (G == 1) {
+        if (P == 4) return launch_k1_inst<MODE, 4, 1>(c, prm, grid, threads, smem);
+        if (P == 2) return launch_k1_inst<MODE, 2, 1>(c, prm, grid, threads, smem);
+        return launch_k1_inst<MODE, 1, 1>(c, prm, grid, threads, smem);
+    }
+    if (G == 8) return launch_k1_inst<MODE, 1, 8>(c, prm, grid, threads, smem);
+    return launch_k1_inst<MODE, 1, 32>(c, prm, grid, threads, smem);
+}
+
+int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, int out_kind,
+                      void* d_out, float step) {
+    c->last_counters[0] = 0;
+    c->last_counters[1] = (int64_t)n_points * (int64_t)c->n_charges;
+    c->last_counters[2] = n_points;
+    if (n_points == 0) return CPET_OK;
+    const Tuning& tu = c->tune;
+    const int sms = c->sm_count;
+
+    int threads = tu.k1_threads > 0 ? tu.k1_threads : 256;
+    if (threads > 256) threads = 256;
+    threads = (threads / 32) * 32;
+    if (threads < 32) threads = 32;
+
+    // lanes per point: enough threads to fill the machine even for tiny grids
+    int G = tu.k1_lanes;
+    if (G <= 0) {
+        const long long full_wave = (long long)sms * 512;
+        if ((long long)n_points >= full_wave) G = 1;
+        else if ((long long)n_points * 8 >= full_wave) G = 8;
+        else G = 32;
+    }
+    if (G != 1 && G != 8 && G != 32) G = (G < 8) ? 8 : 32;
+    int P = tu.k1_points;
+    if (G > 1) P = 1;
+    else if (P <= 0) P = ((long long)n_points >= (long long)sms * 2048) ? 2 : 1;
+    if (P != 1 && P != 2 && P != 4) P = 2;
+
+    const int pts_per_cta = (threads / G) * P;
+    const int gx = (n_points + pts_per_cta - 1) / pts_per_cta;
+
+    // split the charge range when the point dimension alone cannot fill 2 CTAs per SM
+    int splits = tu.k1_splits;
+    if (splits <= 0) {
+        splits = 1;
+        if (gx < 2 * sms) splits = (2 * sms + gx - 1) / gx;
+    }
+    const int min_pairs_per_split = 64;
+    int max_splits = c->n_pairs / min_pairs_per_split;
+    if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 65535) splits = 65535;
+    int pps = (c->n_pairs + splits - 1) / splits;
+    pps = ((pps + 7) / 8) * 8;
+    if (pps < 8) pps = 8;
+    splits = c->n_pairs > 0 ? (c->n_pairs + pps - 1) / pps : 1;
+
+    int tile_pairs = tu.k1_tile_pairs > 0 ? tu.k1_tile_pairs : 1024;
+    if (tile_pairs > pps) tile_pairs = pps;
+    tile_pairs = ((tile_pairs + 7) / 8) * 8;
+    int stages = tu.k1_stages > 0 ? tu.k1_stages : 3;
+    if (stages > 8) stages = 8;
+    const int ntiles = (pps + tile_pairs - 1) / tile_pairs;
+    if (stages > ntiles) stages = ntiles;
+    if (stages < 1) stages = 1;
+    size_t smem = 128 + (size_t)stages * tile_pairs * sizeof(ChargePair);
+    while (smem > (size_t)c->max_smem_optin && tile_pairs > 64) {
+        tile_pairs /= 2;
+        smem = 128 + (size_t)stages * tile_pairs * sizeof(ChargePair);
+    }
+
+    K1Params prm;
+    prm.charges = c->charges.as<ChargePair>();
+    prm.n_pairs = c->n_pairs;
+    prm.pairs_per_split = pps;
+    prm.tile_pairs = tile_pairs;
+    prm.stages = stages;
+    prm.x0 = d_x0;
+    prm.n_points = n_points;
+    prm.out_kind = out_kind;
+    prm.step = step;
+    prm.out = d_out;
+    prm.partial = nullptr;
+    if (splits > 1) {
+        if (int rc = c->work0.reserve(sizeof(double) * 3 * (size_t)splits * (size_t)n_points)) return rc;
+        prm.partial = c->work0.as<double>();
+    }
+
+    KernelTimer timer(c);
+    dim3 grid((unsigned)gx, (unsigned)splits, 1);
+    int rc;
+    if (mode == MODE_FIELD_SOFT) rc = launch_k1_mode<MODE_FIELD_SOFT>(c, prm, P, G, grid, threads, smem);
+    else if (mode == MODE_FIELD_RAW) rc = launch_k1_mode<MODE_FIELD_RAW>(c, prm, P, G, grid, threads, smem);
+    else rc = launch_k1_mode<MODE_ESP>(c, prm, P, G, grid, threads, smem);
+    if (rc) return rc;
+    c->last_counters[0] = 1;
+    if (splits > 1) {
+        k1_finalize_kernel<<<(n_points + 255) / 256, 256, 0, c->stream>>>(
+            prm.partial, splits, n_points, d_x0, out_kind, step, d_out);
+        CPET_CUDA_TRY(cudaGetLastError());
+        c->last_counters[0] = 2;
+    }
+    return CPET_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP32 peak probe: register-resident FMA chains, no memory traffic.
+// ---------------------------------------------------------------------------------------------
+template <int PACKED>
+__global__ void __launch_bounds__(256) fp32_probe_kernel(int iters, float seed, float* sink) {
+    constexpr int CH = 8;
+    if (PACKED) {
+        u64 v[CH];
+        const u64 a = pk2(1.0000001f, 0.9999999f), b = pk2(seed, -seed);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = pk2(seed + i, seed - i);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < CH; ++i) v[i] = fma2(v[i], a, b);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) { float lo, hi; upk2(v[i], lo, hi); s += lo + hi; }
+        if (s == 123.456f) sink[0] = s;
+    } else {
+        float v[2 * CH];
+        const float a = 1.0000001f, b = seed;
+#pragma unroll
+        for (int i = 0; i < 2 * CH; ++i) v[i] = seed + i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 2 * CH; ++i) v[i] = fmaf(v[i], a, b);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2 * CH; ++i) s += v[i];
+        if (s == 123.456f) sink[0] = s;
+    }
+}
+
+int launch_fp32_probe(cpet_ctx* c, int packed, int iters, double* tflops) {
+    if (iters <= 0) iters = 4096;
+    if (int rc = c->work1.reserve(256)) return rc;
+    const int blocks = c->sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CPET_CUDA_TRY(cudaEventCreate(&e0));
+    CPET_CUDA_TRY(cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CPET_CUDA_TRY(cudaEventRecord(e0, c->stream));
+        if (packed) fp32_probe_kernel<1><<<blocks, threads, 0, c->stream>>>(iters, 0.5f, c->work1.as<float>());
+        else fp32_probe_kernel<0><<<blocks, threads, 0, c->stream>>>(iters, 0.5f, c->work1.as<float>());
+        CPET_CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CPET_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CPET_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // per thread: iters * 4 * 16 FMAs (8 packed chains x 2 lanes, or 16 scalar chains)
+    const double fmas = (double)blocks * threads * (double)iters * 4.0 * 16.0;
+    *tflops = 2.0 * fmas / (best_ms * 1e-3) / 1e12;
+    return CPET_OK;
+}
+
+}  // namespace cpet

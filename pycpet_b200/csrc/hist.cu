@@ -1,0 +1,158 @@
+// hist.cu -- K3: batched distance x curvature 2-D histogram with NumPy's binning rule, and the
+// pairwise chi^2 histogram distance.
+//
+// Replaces np.histogram2d as called by make_histograms (CPET/utils/calculator.py:702-707) and
+// distance_numpy / construct_distance_matrix (UC:975-978, 1003-1015).
+//
+// Binning is bit-exact with numpy/lib/_histograms_impl.py::histogramdd: the float64 edge arrays
+// are supplied by the caller (np.linspace), each value is located with a `side='right'` binary
+// search in shared memory, a value equal to the last edge falls in the last bin, outliers (and
+// NaNs) are dropped.  Counting uses warp-aggregated (match.any) shared-memory atomics, flushed
+// once per CTA to 64-bit global counters.
+#include "cpet_internal.h"
+
+namespace cpet {
+
+__device__ __forceinline__ int searchsorted_right(const double* __restrict__ e, int n_edges,
+                                                  double v) {
+    int lo = 0, hi = n_edges;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (e[mid] <= v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <typename T, bool SMEM_COUNTS>
+__global__ void __launch_bounds__(256) k3_hist2d_kernel(const T* __restrict__ values,
+                                                        long long n_per_frame, int nd, int nc,
+                                                        const double* __restrict__ d_edges,
+                                                        const double* __restrict__ c_edges,
+                                                        unsigned long long* __restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* ed = reinterpret_cast<double*>(smem_raw);
+    double* ec = ed + (nd + 1);
+    unsigned* cnt = reinterpret_cast<unsigned*>(ec + (nc + 1));
+    const int nbins = nd * nc;
+    for (int i = threadIdx.x; i <= nd; i += blockDim.x) ed[i] = d_edges[i];
+    for (int i = threadIdx.x; i <= nc; i += blockDim.x) ec[i] = c_edges[i];
+    if (SMEM_COUNTS)
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x) cnt[i] = 0u;
+    __syncthreads();
+
+    const int frame = blockIdx.y;
+    const T* v = values + (size_t)frame * (size_t)n_per_frame * 2;
+    unsigned long long* out = counts + (size_t)frame * (size_t)nbins;
+    const double d_last = ed[nd], c_last = ec[nc];
+
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // keep whole warps in the loop so match.any sees a full mask
+    const long long n_round = ((n_per_frame + 31) / 32) * 32;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        int bin = -1;
+        if (i < n_per_frame) {
+            const double d = (double)v[2 * i], c = (double)v[2 * i + 1];
+            int bi = searchsorted_right(ed, nd + 1, d);
+            int bj = searchsorted_right(ec, nc + 1, c);
+            if (d == d_last) --bi;
+            if (c == c_last) --bj;
+            if (bi >= 1 && bi <= nd && bj >= 1 && bj <= nc) bin = (bi - 1) * nc + (bj - 1);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, bin);
+        if (bin >= 0) {
+            const int lane = threadIdx.x & 31;
+            if (lane == __ffs(peers) - 1) {
+                const unsigned add = (unsigned)__popc(peers);
+                if (SMEM_COUNTS) atomicAdd(&cnt[bin], add);
+                else atomicAdd(&out[bin], (unsigned long long)add);
+            }
+        }
+    }
+    if (SMEM_COUNTS) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x)
+            if (cnt[i]) atomicAdd(&out[i], (unsigned long long)cnt[i]);
+    }
+}
+
+int launch_hist2d(cpet_ctx* c, int n_frames, int64_t n_per_frame, const void* d_values,
+                  bool values_f64, int nd, const double* d_edges_dev, int nc,
+                  const double* c_edges_dev, unsigned long long* d_counts) {
+    c->last_counters[0] = 0;
+    c->last_counters[1] = 0;
+    c->last_counters[2] = 0;
+    const size_t nbins = (size_t)nd * nc;
+    CPET_CUDA_TRY(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * nbins * n_frames, c->stream));
+    if (n_frames == 0 || n_per_frame == 0 || nbins == 0) return CPET_OK;
+    const size_t edge_bytes = sizeof(double) * (size_t)(nd + nc + 2);
+    const size_t smem_counts = edge_bytes + sizeof(unsigned) * nbins;
+    const bool in_smem = smem_counts <= (size_t)c->max_smem_optin;
+    const size_t smem = in_smem ? smem_counts : edge_bytes;
+    CPET_REQUIRE(edge_bytes <= (size_t)c->max_smem_optin, CPET_ERR_INVALID,
+                 "histogram edges do not fit in shared memory (nd=%d nc=%d)", nd, nc);
+    long long bx = (n_per_frame + 256 * 8 - 1) / (256 * 8);
+    const long long cap = (long long)c->sm_count * 8 / (n_frames < 1 ? 1 : n_frames) + 1;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)n_frames, 1);
+    KernelTimer timer(c);
+#define CPET_K3_LAUNCH(T, S)                                                                   \
+    do {                                                                                       \
+        auto kern = k3_hist2d_kernel<T, S>;                                                    \
+        CPET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                           (int)smem));                                        \
+        kern<<<grid, 256, smem, c->stream>>>((const T*)d_values, (long long)n_per_frame, nd,   \
+                                             nc, d_edges_dev, c_edges_dev, d_counts);          \
+    } while (0)
+    if (values_f64) { if (in_smem) CPET_K3_LAUNCH(double, true); else CPET_K3_LAUNCH(double, false); }
+    else            { if (in_smem) CPET_K3_LAUNCH(float, true);  else CPET_K3_LAUNCH(float, false); }
+#undef CPET_K3_LAUNCH
+    CPET_CUDA_TRY(cudaGetLastError());
+    c->last_counters[0] = 1;
+    return CPET_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// chi^2 distance matrix: one CTA per (i, j>i) pair, FP64.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chi2_kernel(const double* __restrict__ H, int n,
+                                                   long long nbins, double* __restrict__ out) {
+    const int i = blockIdx.y, j = blockIdx.x;
+    if (j < i) return;
+    if (j == i) { if (threadIdx.x == 0) out[(size_t)i * n + i] = 0.0; return; }
+    const double* a = H + (size_t)i * nbins;
+    const double* b = H + (size_t)j * nbins;
+    double s = 0.0;
+    for (long long k = threadIdx.x; k < nbins; k += blockDim.x) {
+        const double x = a[k], y = b[k];
+        const double sum = x + y;
+        const double diff = x - y;
+        if (sum != 0.0) s += diff * diff / sum;
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w >= 1; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double d = 0.5 * red[0];
+        out[(size_t)i * n + j] = d;
+        out[(size_t)j * n + i] = d;
+    }
+}
+
+int launch_chi2(cpet_ctx* c, int n_hists, int64_t n_bins, const double* d_H, double* d_out) {
+    c->last_counters[0] = 0;
+    if (n_hists == 0) return CPET_OK;
+    CPET_REQUIRE(n_hists <= 65535, CPET_ERR_INVALID, "chi2 matrix limited to 65535 histograms");
+    KernelTimer timer(c);
+    dim3 grid((unsigned)n_hists, (unsigned)n_hists, 1);
+    chi2_kernel<<<grid, 256, 0, c->stream>>>(d_H, n_hists, (long long)n_bins, d_out);
+    CPET_CUDA_TRY(cudaGetLastError());
+    c->last_counters[0] = 1;
+    return CPET_OK;
+}
+
+}  // namespace cpet

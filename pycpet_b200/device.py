@@ -1,0 +1,156 @@
+"""Device-pointer API: torch CUDA tensors in, torch CUDA tensors out, no host copies, no syncs.
+
+PyTorch is plumbing only here (device memory, streams, torch.distributed buffers); the math is
+the ``*_dev`` entry points of libcpetb200.so, run on torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One context bound to (device, torch's current stream on that device)."""
+
+    def __init__(self, device=None, stream=None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise _lib.CpetError("Engine needs a CUDA device (no CPU fallback)")
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.lib = _lib.load()
+        with torch.cuda.device(self.device):
+            self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+            h = ctypes.c_void_p()
+            check(self.lib.cpet_create_on_stream(self.device.index, ctypes.c_void_p(self.stream.cuda_stream),
+                                                 ctypes.byref(h)))
+        self.ctx = h
+        self.n_charges = 0
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None:
+            self.lib.cpet_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _f32(self, t, cols=None):
+        torch = self.torch
+        t = torch.as_tensor(t, device=self.device) if not torch.is_tensor(t) else t
+        if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        if cols is not None:
+            t = t.reshape(-1, cols)
+        return t
+
+    def set_tuning(self, **kv):
+        for k, v in kv.items():
+            check(self.lib.cpet_set_tuning(self.ctx, k.encode(), int(v)))
+
+    def last_counters(self):
+        out = (ctypes.c_int64 * 3)()
+        check(self.lib.cpet_last_counters(self.ctx, out))
+        return {"launches": int(out[0]), "pair_evals": int(out[1]), "field_evals": int(out[2])}
+
+    def last_kernel_ms(self) -> float:
+        ms = ctypes.c_double(0.0)
+        check(self.lib.cpet_last_kernel_ms(self.ctx, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def fp32_peak_tflops(self, packed=True, iters=4096) -> float:
+        t = ctypes.c_double(0.0)
+        check(self.lib.cpet_fp32_peak_probe(self.ctx, int(bool(packed)), int(iters), ctypes.byref(t)))
+        return float(t.value)
+
+    # -- the path --------------------------------------------------------------------------------
+    def set_charges(self, x, Q):
+        x = self._f32(x, 3)
+        Q = self._f32(Q).reshape(-1)
+        assert x.shape[0] == Q.shape[0]
+        check(self.lib.cpet_set_charges_dev(self.ctx, x.shape[0], _p(x), _p(Q)))
+        self.n_charges = x.shape[0]
+        self._keep = (x, Q)          # the pack kernel reads them asynchronously
+
+    def field_grid(self, x0, soften=True, concat=False, out=None):
+        torch = self.torch
+        x0 = self._f32(x0, 3)
+        n = x0.shape[0]
+        if out is None:
+            out = torch.empty((n, 6 if concat else 3), dtype=torch.float32, device=self.device)
+        flags = (_lib.CPET_FIELD_SOFTEN if soften else 0) | (_lib.CPET_OUT_CONCAT if concat else 0)
+        check(self.lib.cpet_field_grid_dev(self.ctx, n, _p(x0), flags, _p(out)))
+        return out
+
+    def esp_grid(self, x0, concat_half=False, out=None):
+        torch = self.torch
+        x0 = self._f32(x0, 3)
+        n = x0.shape[0]
+        if out is None:
+            out = (torch.empty((n, 4), dtype=torch.float16, device=self.device) if concat_half
+                   else torch.empty(n, dtype=torch.float32, device=self.device))
+        check(self.lib.cpet_esp_grid_dev(self.ctx, n, _p(x0), _lib.CPET_OUT_CONCAT if concat_half else 0,
+                                         _p(out)))
+        return out
+
+    def propagate(self, x0, step_size, out=None):
+        torch = self.torch
+        x0 = self._f32(x0, 3)
+        if out is None:
+            out = torch.empty_like(x0)
+        check(self.lib.cpet_propagate_dev(self.ctx, x0.shape[0], _p(x0), float(step_size), _p(out)))
+        return out
+
+    def topo_batch(self, seeds, n_iter, step_size, dimensions, second_diff=False, out=None,
+                   steps=None, want_steps=False):
+        torch = self.torch
+        seeds = self._f32(seeds, 3)
+        n = seeds.shape[0]
+        if not torch.is_tensor(n_iter):
+            n_iter = torch.as_tensor(np.asarray(n_iter).astype(np.int32), device=self.device)
+        if n_iter.dtype != torch.int32 or n_iter.device != self.device:
+            n_iter = n_iter.to(device=self.device, dtype=torch.int32)
+        n_iter = n_iter.contiguous().reshape(-1)
+        assert n_iter.shape[0] == n
+        dims = (ctypes.c_float * 3)(*[float(v) for v in np.asarray(dimensions).reshape(3)])
+        if out is None:
+            out = torch.empty((n, 2), dtype=torch.float32, device=self.device)
+        if want_steps and steps is None:
+            steps = torch.empty(n, dtype=torch.int32, device=self.device)
+        check(self.lib.cpet_topo_batch_dev(
+            self.ctx, n, _p(seeds), _p(n_iter), float(step_size), dims,
+            _lib.CPET_TOPO_CURV_SECOND_DIFF if second_diff else 0, _p(out),
+            _p(steps) if steps is not None else None))
+        self._keep2 = (seeds, n_iter)
+        return (out, steps) if want_steps else out
+
+    def hist2d(self, values, d_edges, c_edges, out=None):
+        """values: (F, n, 2) or (n, 2) float32 CUDA tensor -> (F, nd, nc) / (nd, nc) int64."""
+        torch = self.torch
+        v = self._f32(values)
+        single = v.dim() == 2
+        if single:
+            v = v.unsqueeze(0)
+        assert v.dim() == 3 and v.shape[2] == 2
+        de = np.ascontiguousarray(d_edges, dtype=np.float64)
+        ce = np.ascontiguousarray(c_edges, dtype=np.float64)
+        nd, nc = de.shape[0] - 1, ce.shape[0] - 1
+        if out is None:
+            out = torch.empty((v.shape[0], nd, nc), dtype=torch.int64, device=self.device)
+        check(self.lib.cpet_hist2d_dev(self.ctx, v.shape[0], v.shape[1], _p(v), nd, _lib.ptr(de), nc,
+                                       _lib.ptr(ce), _p(out)))
+        self._keep3 = (v, de, ce)
+        return out[0] if single else out

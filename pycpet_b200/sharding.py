@@ -1,0 +1,194 @@
+"""Multi-GPU layer: one process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).
+
+The path shards with no data-path collective: every grid point, every streamline and every MD
+frame is independent and needs only the (replicated, <= 16 MB) charge set of its frame
+(SURVEY.md section 8e).  Collectives appear once, at the end:
+
+  * fields / ESP      : all_gather of per-rank slabs of the flattened point list
+  * single-frame topo : all_gather of per-rank (line id, dist, curv) rows, restored to seed order
+  * histograms        : all_reduce(sum) of int64 bin counts; all_reduce(min/max) for global ranges
+  * MD-frame batches  : frames dealt round-robin, per-frame results gathered by frame id
+
+Partitioning and collectives are independent of who computes: each function takes a `compute`
+callable working on the local shard (``Engine`` methods in production; the CPU tests drive the
+same code over gloo with world_size 2).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def world():
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def slab(n: int, rank: int, size: int):
+    """Contiguous slab [lo, hi) of n items for `rank`; sizes differ by at most one."""
+    base, rem = divmod(int(n), int(size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def frames_for_rank(n_frames: int, rank: int, size: int):
+    """MD frames dealt round-robin (frame f -> rank f % size)."""
+    return list(range(rank, int(n_frames), size))
+
+
+def deal_lines(n_iter, rank: int, size: int, block: int = 32):
+    """Line ids of this rank for a single-frame topology: lines sorted by n_iter (descending,
+    stable) and dealt round-robin in warp-sized blocks, so every rank gets the same mix of long
+    and short lines (cost is proportional to the steps taken)."""
+    n_iter = np.asarray(n_iter).reshape(-1)
+    order = np.argsort(-n_iter, kind="stable")
+    nblk = (len(order) + block - 1) // block
+    mine = []
+    for b in range(nblk):
+        rnd, pos = divmod(b, size)
+        owner = pos if (rnd % 2 == 0) else size - 1 - pos      # serpentine: cancels the sort bias
+        if owner == rank:
+            mine.append(order[b * block:(b + 1) * block])
+    return np.concatenate(mine) if mine else np.zeros(0, dtype=np.int64)
+
+
+def _device_of(backend_tensor_device):
+    return backend_tensor_device
+
+
+def _comm_device():
+    """Tensors handed to collectives live on the GPU for NCCL and on the host for gloo."""
+    import torch
+
+    dist = _dist()
+    if dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def all_gather_rows(local, counts=None):
+    """Concatenate per-rank row blocks (different lengths allowed) on every rank."""
+    import torch
+
+    dist = _dist()
+    rank, size = world()
+    t = local if torch.is_tensor(local) else torch.as_tensor(np.ascontiguousarray(local))
+    if size == 1:
+        return t
+    dev = _comm_device()
+    t = t.to(dev).contiguous()
+    n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=dev)
+    ns = [torch.zeros_like(n_local) for _ in range(size)]
+    dist.all_gather(ns, n_local)
+    ns = [int(v.item()) for v in ns]
+    n_max = max(ns)
+    pad = torch.zeros((n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+    pad[: t.shape[0]] = t
+    bufs = [torch.empty_like(pad) for _ in range(size)]
+    dist.all_gather(bufs, pad)
+    return torch.cat([b[:n] for b, n in zip(bufs, ns)], dim=0)
+
+
+def all_reduce_(t, op="sum"):
+    import torch
+
+    dist = _dist()
+    _, size = world()
+    if size == 1:
+        return t
+    ops = {"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}
+    dev = _comm_device()
+    buf = t.to(dev).contiguous()
+    dist.all_reduce(buf, op=ops[op])
+    if buf.data_ptr() != t.data_ptr():
+        t.copy_(buf)
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+def grid_sharded(compute, x0):
+    """Field / ESP over a point list sharded by slabs.
+    compute(points_slab) -> rows for that slab (torch tensor or ndarray, first dim = points).
+    Returns the full result, identical on every rank, in point order."""
+    rank, size = world()
+    lo, hi = slab(len(x0), rank, size)
+    return all_gather_rows(compute(x0[lo:hi]))
+
+
+def topo_sharded(compute, seeds, n_iter):
+    """Single-frame topology sharded by streamlines.
+    compute(seeds_subset, n_iter_subset) -> (n,2) [dist|curv] rows in the order given.
+    Returns (L,2) in SEED order on every rank."""
+    import torch
+
+    rank, size = world()
+    seeds = np.asarray(seeds).reshape(-1, 3)
+    n_iter = np.asarray(n_iter).reshape(-1)
+    ids = deal_lines(n_iter, rank, size)
+    local = compute(seeds[ids], n_iter[ids])
+    local = local if torch.is_tensor(local) else torch.as_tensor(np.ascontiguousarray(local))
+    idt = torch.as_tensor(ids.astype(np.int64)).to(local.device)
+    rows = torch.cat([idt.to(torch.float64).unsqueeze(1), local.to(torch.float64)], dim=1)
+    allrows = all_gather_rows(rows)
+    out = torch.empty((len(seeds), 2), dtype=local.dtype, device=allrows.device)
+    out[allrows[:, 0].to(torch.int64)] = allrows[:, 1:].to(local.dtype)
+    return out
+
+
+def hist_sharded(compute_counts, values_local, d_edges, c_edges):
+    """Histogram of a line set spread over ranks: local counts then all_reduce(sum)."""
+    import torch
+
+    counts = compute_counts(values_local, d_edges, c_edges)
+    counts = counts if torch.is_tensor(counts) else torch.as_tensor(np.ascontiguousarray(counts))
+    return all_reduce_(counts.clone(), "sum")
+
+
+def global_ranges(values_local):
+    """(dmin, dmax, cmin, cmax) over all ranks -- the global ranges make_histograms needs
+    (CPET/utils/calculator.py:664-667)."""
+    import torch
+
+    v = values_local if torch.is_tensor(values_local) else torch.as_tensor(np.asarray(values_local))
+    v = v.reshape(-1, 2).to(torch.float64)
+    if v.shape[0]:
+        lo = v.min(dim=0).values
+        hi = v.max(dim=0).values
+    else:
+        lo = torch.full((2,), float("inf"), dtype=torch.float64)
+        hi = torch.full((2,), float("-inf"), dtype=torch.float64)
+    lo = all_reduce_(lo.clone(), "min")
+    hi = all_reduce_(hi.clone(), "max")
+    return float(lo[0]), float(hi[0]), float(lo[1]), float(hi[1])
+
+
+def frames_sharded(compute_frame, n_frames):
+    """MD-frame batch: this rank runs compute_frame(f) for f = rank, rank+size, ...; the per-frame
+    results (equal-shaped arrays/tensors) are gathered and returned stacked in frame order."""
+    import torch
+
+    rank, size = world()
+    mine = frames_for_rank(n_frames, rank, size)
+    res = [compute_frame(f) for f in mine]
+    res = [r if torch.is_tensor(r) else torch.as_tensor(np.ascontiguousarray(r)) for r in res]
+    if size == 1:
+        return torch.stack(res) if res else torch.zeros(0)
+    shape = tuple(res[0].shape) if res else None
+    shapes = [None] * size
+    _dist().all_gather_object(shapes, shape)
+    shape = next(s for s in shapes if s is not None)
+    dtype = res[0].dtype if res else torch.float32
+    flat = (torch.stack(res).reshape(len(res), -1) if res
+            else torch.zeros((0, int(np.prod(shape))), dtype=dtype))
+    ids = torch.as_tensor(np.asarray(mine, dtype=np.float64)).reshape(-1, 1).to(flat.device)
+    rows = all_gather_rows(torch.cat([ids, flat.to(torch.float64)], dim=1))
+    out = torch.empty((n_frames,) + shape, dtype=flat.dtype, device=rows.device)
+    out[rows[:, 0].to(torch.int64)] = rows[:, 1:].to(flat.dtype).reshape((-1,) + shape)
+    return out

@@ -1,0 +1,80 @@
+"""CPU: the C-ABI library loads and exports every symbol include/cpet_b200.h declares; the
+reference-shaped binding class constructs on it; compute calls fail loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    txt = open(os.path.join(ROOT, "include", "cpet_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|void|char)\s*\*?\s*(\w+)\s*\(", txt, flags=re.M)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+    from pycpet_b200 import _lib
+
+    L = _lib.load()
+    names = header_functions()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/cpet_b200.h but not exported"
+    # every symbol bound by the Python layer is declared in the header
+    for n in list(_lib.SIGNATURES) + _lib.LEGACY_SYMBOLS:
+        assert n in names, f"{n} bound in _lib.py but not declared in the header"
+    assert L.cpet_abi_version() == 1
+
+
+def test_reference_symbols_present():
+    """Math_ops.__init__ of the reference sets argtypes on these names (c_ops.py:26-159)."""
+    from pycpet_b200 import _lib
+
+    L = _lib.load()
+    for n in ["sparse_dot", "vecaddn", "dot", "einsum_ij_i", "einsum_ij_i_batch",
+              "einsum_operation_batch", "einsum_operation", "thread_operation",
+              "thread_operation_dipole", "calc_field", "calc_field_base", "calc_esp_base",
+              "compute_batched_field", "compute_looped_field"]:
+        assert hasattr(L, n)
+
+
+def test_math_ops_constructs_and_rejects_bad_arrays():
+    from pycpet_b200 import Math_ops
+
+    m = Math_ops()
+    x = np.zeros((4, 3), dtype=np.float64)      # wrong dtype: ndpointer must reject it
+    q = np.zeros(4, dtype=np.float32)
+    with pytest.raises(ctypes.ArgumentError):
+        m.math.calc_field(np.zeros(3, dtype=np.float32), np.zeros(3, dtype=np.float32), 4, x, q)
+    with pytest.raises(ctypes.ArgumentError):   # wrong ndim
+        m.math.compute_looped_field(1, 4, np.zeros(3, dtype=np.float32), x.astype(np.float32), q,
+                                    np.zeros((1, 3), dtype=np.float32))
+
+
+def test_no_silent_fallback_without_gpu():
+    from pycpet_b200 import CpetError, Math_ops, _lib
+
+    if _lib.load().cpet_device_count() > 0:
+        pytest.skip("a GPU is present")
+    m = Math_ops()
+    with pytest.raises(CpetError):
+        m.field_grid(np.zeros((2, 3), np.float32), np.ones((4, 3), np.float32), np.ones(4, np.float32))
+    with pytest.raises(CpetError):
+        m.compute_looped_field(np.zeros((2, 3), np.float32), np.ones((4, 3), np.float32),
+                               np.ones(4, np.float32))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under pycpet_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "pycpet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert "libcpet_oracle" not in src and "oracle/_ref" not in src, f

@@ -1,0 +1,493 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C-ABI
+(ctypes, include/cpet_b200.h), against the float64 oracle, the reference-generated golden vectors
+and size-independent properties.  /root/reference is NOT needed here.
+
+Tolerances (BASELINE.json north_star):
+  field / ESP : max-norm relative error vs the float64 oracle <= 1e-5
+  streamlines : |dist - oracle| <= 2e-6 (fraction of step-count flips <= 1e-3);
+                |curv - oracle| <= 5e-5 + 2e-7/h^2  (reference-style FP32 second differences)
+                and <= 2e-5 + 2e-6/h for the default direction-based curvature
+  histogram   : bit-exact vs np.histogram2d
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import f64, hist as ohist
+
+pytestmark = pytest.mark.gpu
+
+FIELD_TOL = 1e-5
+
+
+def relmax(a, b):
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - b)) / np.max(np.abs(b)))
+
+
+@pytest.fixture(scope="module")
+def M():
+    from pycpet_b200 import Math_ops
+
+    m = Math_ops()
+    yield m
+    m.close()
+
+
+@pytest.fixture(scope="module")
+def frame2a(golden):
+    g = golden("example_2A_volume.npz")
+    return g["x"], g["Q"].reshape(-1)
+
+
+def reset_tuning(m):
+    m.set_tuning(k1_threads=0, k1_points=0, k1_lanes=0, k1_tile_pairs=0, k1_stages=0, k1_splits=0,
+                 k2_threads=0, k2_lanes=0, k2_tile_pairs=0, k2_stages=0, k2_sort=-1)
+
+
+# ------------------------------------------------------------------------------------ K1 --------
+def test_field_example_2A(M, golden, frame2a):
+    g = golden("example_2A_volume.npz")
+    x, Q = frame2a
+    out = M.field_grid(g["mesh"].reshape(-1, 3), x, Q, soften=True, concat=True)
+    assert out.shape == (1331, 6) and out.dtype == np.float32
+    np.testing.assert_array_equal(out[:, :3], g["mesh"].reshape(-1, 3))
+    e = f64.field_grid(g["mesh"].reshape(-1, 3), x, Q, True)
+    assert relmax(out[:, 3:], e) < FIELD_TOL
+    # and against what the unmodified reference produced for this input (calculator.compute_box)
+    assert relmax(out[:, 3:], g["field_box"][:, 3:]) < FIELD_TOL
+    c = M.last_counters()
+    assert c["pair_evals"] == 1331 * 7890 and c["launches"] >= 1
+
+
+def test_point_field_example_1A_known_answer(M, golden):
+    g = golden("example_1A_point_field.npz")
+    e = M.calc_field(g["point"], g["x"], g["Q"].reshape(-1))
+    # examples/1A_point-field/outdir/point_field.dat (the reference's only exact shipped answer)
+    np.testing.assert_allclose(e, g["shipped_point_field_dat"], rtol=2e-5)
+    np.testing.assert_allclose(e, g["field"], rtol=2e-5)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(k1_points=1, k1_lanes=1), dict(k1_points=2, k1_lanes=1), dict(k1_points=4, k1_lanes=1),
+    dict(k1_lanes=8), dict(k1_lanes=32), dict(k1_lanes=1, k1_splits=1), dict(k1_lanes=32, k1_splits=7),
+    dict(k1_points=2, k1_lanes=1, k1_tile_pairs=64, k1_stages=2),
+    dict(k1_points=1, k1_lanes=8, k1_tile_pairs=128, k1_stages=4, k1_splits=3),
+    dict(k1_threads=64, k1_points=4, k1_lanes=1, k1_tile_pairs=256, k1_stages=8),
+])
+@pytest.mark.parametrize("mode", ["soft", "raw", "esp"])
+def test_field_all_kernel_variants(M, cfg, mode):
+    x, Q = synth.charges(5001, seed=11, box=1.0)          # odd count: exercises the pad charge
+    pts = synth.grid(9, 1.0)                               # 729 points
+    reset_tuning(M)
+    M.set_tuning(**cfg)
+    try:
+        if mode == "esp":
+            got = M.esp_grid(pts, x, Q)
+            want = f64.esp_grid(pts, x, Q)
+        else:
+            got = M.field_grid(pts, x, Q, soften=(mode == "soft"))
+            want = f64.field_grid(pts, x, Q, mode == "soft")
+        assert relmax(got, want) < FIELD_TOL
+    finally:
+        reset_tuning(M)
+
+
+def test_field_synthetic_golden_and_softening(M, golden):
+    g = golden("synthetic_math_ops.npz")
+    x, Q = g["x"], g["Q"]
+    got = M.compute_looped_field(g["points"], x, Q)
+    assert relmax(got, f64.field_grid(g["points"], x, Q, True)) < FIELD_TOL
+    assert relmax(got, g["looped_field"]) < FIELD_TOL
+    # grid points sitting exactly on charges: softened field is finite and matches (C:433)
+    gs = M.compute_looped_field(g["points_soft"], x, Q)
+    assert np.all(np.isfinite(gs))
+    assert relmax(gs, f64.field_grid(g["points_soft"], x, Q, True)) < FIELD_TOL
+    # without softening a point on a charge is NaN/inf exactly like calc_field_base (C:318-319)
+    raw = M.field_grid(g["points_soft"][:3], x, Q, soften=False)
+    assert not np.all(np.isfinite(raw))
+    # compute_batched_field = no softening
+    nb = M.compute_batch_field(g["points"], x, Q, 100)
+    assert relmax(nb, f64.field_grid(g["points"], x, Q, False)) < FIELD_TOL
+
+
+def test_esp_example_2A(M, golden, frame2a):
+    ge = golden("example_2A_volume_esp.npz")
+    x, Q = frame2a
+    pts = ge["mesh"].reshape(-1, 3)
+    phi = f64.esp_grid(pts, x, Q)
+    got = M.esp_grid(pts, x, Q)
+    assert relmax(got, phi) < FIELD_TOL
+    box = M.esp_grid(pts, x, Q, concat_half=True)
+    assert box.dtype == np.float16 and box.shape == (1331, 4)
+    np.testing.assert_array_equal(box[:, :3], pts.astype(np.float16))
+    # float64 -> float32 -> float16 like the reference; equal to the oracle's cast except where
+    # a 1e-6-relative difference straddles a float16 rounding boundary
+    want16 = phi.astype(np.float32).astype(np.float16)
+    mism = box[:, 3] != want16
+    assert mism.mean() < 0.01
+    ulp = np.spacing(np.abs(want16)).astype(np.float64)
+    assert np.all(np.abs(box[:, 3].astype(np.float64) - want16.astype(np.float64)) <= ulp)
+    # the reference's own float16 output for this frame (compute_box_ESP)
+    ref_box = ge["esp_box"]
+    assert np.mean(box[:, 3] != ref_box[:, 3]) < 0.05
+    assert np.all(np.abs(box[:, 3].astype(np.float64) - ref_box[:, 3].astype(np.float64)) <= ulp)
+
+
+def test_field_edge_cases(M):
+    x, Q = synth.charges(33, seed=2, box=0.5)
+    pts = synth.grid(3, 0.5)
+    # empty point list, single point, single charge
+    assert M.field_grid(np.zeros((0, 3), np.float32), x, Q).shape == (0, 3)
+    one = M.field_grid(pts[:1], x, Q, soften=False)
+    assert relmax(one, f64.field_grid(pts[:1], x, Q, False)) < FIELD_TOL
+    e1 = M.field_grid(pts, x[:1], Q[:1], soften=False)
+    assert relmax(e1, f64.field_grid(pts, x[:1], Q[:1], False)) < FIELD_TOL
+    # ragged sizes around the tile / pair / warp boundaries
+    for m in (2, 3, 127, 128, 129, 2047, 2049):
+        xm, qm = synth.charges(m, seed=m, box=0.5)
+        for n in (1, 31, 33, 257):
+            p = np.random.default_rng(n).uniform(-0.5, 0.5, (n, 3)).astype(np.float32)
+            assert relmax(M.field_grid(p, xm, qm, soften=True), f64.field_grid(p, xm, qm, True)) < FIELD_TOL
+
+
+def test_field_accumulation_at_100k_charges(M):
+    """Heavy +/- cancellation (net-neutral 100k charges): FP32-in-tile / FP64-across-tiles holds
+    1e-5 where a plain FP32 sequential sum (the reference) does not."""
+    x, Q = synth.charges(100_000, seed=3, box=5.0)
+    pts = synth.grid(8, 5.0)
+    assert relmax(M.field_grid(pts, x, Q, soften=True), f64.field_grid(pts, x, Q, True)) < FIELD_TOL
+    assert relmax(M.esp_grid(pts, x, Q), f64.esp_grid(pts, x, Q)) < FIELD_TOL
+
+
+def test_field_full_size_properties(M):
+    """ESP configuration size (101^3 points) on a 20k-charge frame: exact linearity in Q by powers
+    of two, invariance to point order, and oracle parity on a random sample of points."""
+    x, Q = synth.charges(20_000, seed=4, box=5.0)
+    pts = synth.grid(101, 5.0)
+    assert len(pts) == 101 ** 3
+    M.set_charges(x, Q)
+    e = M.field_grid(pts, soften=True)
+    M.set_charges(x, 2.0 * Q)
+    e2 = M.field_grid(pts, soften=True)
+    np.testing.assert_array_equal(e2, 2.0 * e)                      # bit-exact scaling
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(len(pts))
+    M.set_charges(x, Q)
+    ep = M.field_grid(pts[perm], soften=True)
+    np.testing.assert_array_equal(ep, e[perm])                      # per-point independence
+    idx = rng.choice(len(pts), 2000, replace=False)
+    assert relmax(e[idx], f64.field_grid(pts[idx], x, Q, True)) < FIELD_TOL
+    phi = M.esp_grid(pts)
+    assert relmax(phi[idx], f64.esp_grid(pts[idx], x, Q)) < FIELD_TOL
+
+
+def test_propagate(M, frame2a):
+    x, Q = frame2a
+    pts = synth.grid(4, 0.4)
+    got = M.propagate(pts, 0.1, x, Q)
+    want = np.array([f64.step(p, 0.1, x, Q) for p in pts])
+    assert np.max(np.abs(got - want)) < 2e-7
+    from pycpet_b200 import calculator as calc
+    one = calc.propagate_topo(pts[3], x, Q, 0.1)
+    np.testing.assert_array_equal(one, got[3])
+
+
+# ------------------------------------------------------------------------------------ K2 --------
+def curv_tol_sd(h):
+    return 5e-5 + 2e-7 / h ** 2
+
+
+def curv_tol_dir(h):
+    return 2e-5 + 2e-6 / h
+
+
+def check_lines(got, steps, want, wsteps, h, tol_curv):
+    flips = steps != wsteps
+    assert flips.mean() <= 1e-3 or flips.sum() <= 1
+    ok = ~flips
+    assert np.max(np.abs(got[ok, 0] - want[ok, 0])) <= 2e-6
+    assert np.max(np.abs(got[ok, 1] - want[ok, 1])) <= tol_curv
+
+
+def test_topo_example_3A(M, golden, frame2a):
+    t = golden("example_3A_topo.npz")
+    x, Q = frame2a
+    h = float(t["step_size"])
+    want, wsteps = f64.topo_batch(t["seeds"], t["n_iter"], x, Q, h, t["dimensions"])
+    got, steps = M.topo_batch(t["seeds"], t["n_iter"], x, Q, h, t["dimensions"], want_steps=True)
+    assert got.shape == (216, 2) and got.dtype == np.float32
+    check_lines(got, steps, want, wsteps, h, curv_tol_dir(h))
+    got_sd, steps_sd = M.topo_batch(t["seeds"], t["n_iter"], x, Q, h, t["dimensions"], second_diff=True,
+                                    want_steps=True)
+    check_lines(got_sd, steps_sd, want, wsteps, h, curv_tol_sd(h))
+    # the unmodified reference's output for the same seeded run (compute_topo_complete_c_shared)
+    ref = t["hist"]
+    assert np.max(np.abs(got[:, 0] - ref[:, 0])) <= 2e-6
+    assert np.max(np.abs(got[:, 1] - ref[:, 1])) <= curv_tol_sd(h)
+    c = M.last_counters()
+    assert c["field_evals"] == int((steps_sd + 2).sum())
+    assert c["pair_evals"] == c["field_evals"] * 7890
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(k2_lanes=1), dict(k2_lanes=2), dict(k2_lanes=4), dict(k2_lanes=8), dict(k2_lanes=16),
+    dict(k2_lanes=32), dict(k2_lanes=1, k2_threads=64, k2_sort=1), dict(k2_lanes=4, k2_sort=0),
+    dict(k2_lanes=1, k2_tile_pairs=256, k2_stages=2),          # forces the streamed charge ring
+    dict(k2_lanes=8, k2_tile_pairs=512, k2_stages=3, k2_threads=128),
+    dict(k2_lanes=32, k2_tile_pairs=64, k2_stages=4),
+])
+def test_topo_all_kernel_variants(M, golden, cfg):
+    g = golden("synthetic_math_ops.npz")
+    x, Q = g["x"], g["Q"]
+    reset_tuning(M)
+    M.set_tuning(**cfg)
+    try:
+        for h in (0.1, 0.01):
+            n_iter = g[f"n_iter_h{h}"]
+            want, wsteps = f64.topo_batch(g["seeds"], n_iter, x, Q, h, g["dimensions"])
+            got, steps = M.topo_batch(g["seeds"], n_iter, x, Q, h, g["dimensions"], want_steps=True)
+            check_lines(got, steps, want, wsteps, h, curv_tol_dir(h))
+            got, steps = M.topo_batch(g["seeds"], n_iter, x, Q, h, g["dimensions"], second_diff=True,
+                                      want_steps=True)
+            check_lines(got, steps, want, wsteps, h, curv_tol_sd(h))
+            # against the reference's own FP32 output (its deviation from float64 is ~1e-7/h^2)
+            ref = g[f"lines_h{h}"]
+            ok = np.abs(got[:, 0] - ref[:, 0]) < h / 2
+            assert ok.mean() > 0.95
+            assert np.max(np.abs(got[ok, 1] - ref[ok, 1])) <= 2 * curv_tol_sd(h)
+    finally:
+        reset_tuning(M)
+
+
+def test_topo_streamed_charges_large_frame(M):
+    """M = 30k charges does not fit in shared memory: tiles stream through the TMA ring."""
+    x, Q = synth.charges(30_000, seed=6, box=0.5)
+    seeds, n_iter, dims, _ = synth.seeds(7, 0.5, 0.1)            # 343 lines
+    want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
+    got, steps = M.topo_batch(seeds, n_iter, x, Q, 0.1, dims, want_steps=True)
+    check_lines(got, steps, want, wsteps, 0.1, curv_tol_dir(0.1))
+
+
+def test_topo_edge_cases(M, frame2a):
+    x, Q = frame2a
+    dims = np.array([0.5, 0.5, 0.5], np.float32)
+    assert M.topo_batch(np.zeros((0, 3), np.float32), np.zeros(0, np.int32), x, Q, 0.1, dims).shape == (0, 2)
+    # one line, n_iter = 1 and a seed that leaves the box on its first step
+    seeds = np.array([[0.0, 0.0, 0.0], [0.499, 0.499, 0.499], [-0.499, 0.3, 0.1]], np.float32)
+    for n_it in (1, 2, 50):
+        n_iter = np.full(3, n_it)
+        want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
+        got, steps = M.topo_batch(seeds, n_iter, x, Q, 0.1, dims, want_steps=True)
+        np.testing.assert_array_equal(steps, wsteps)
+        assert np.max(np.abs(got - want)) < 5e-5
+    # the per-line legacy entry point (thread_operation) gives the same numbers as the batch
+    one = M.thread_operation(seeds[2], 50, x, Q, 0.1, dims)
+    np.testing.assert_allclose(one, got[2], rtol=0, atol=2e-6)
+    # n_iter = 0: no step taken, distance exactly 0
+    z = M.topo_batch(seeds, np.zeros(3, np.int32), x, Q, 0.1, dims)
+    assert np.all(z[:, 0] == 0.0) and np.all(np.isfinite(z[:, 1]))
+
+
+def test_topo_full_size_3A_properties(M, frame2a):
+    """Configuration 3A at the size BASELINE.json names (47^3 = 103,823 seeds, h = 0.1, 17 max
+    steps): invariants + order independence + oracle parity on a sample."""
+    x, Q = frame2a
+    seeds, n_iter, dims, max_steps = synth.seeds(47, 0.5, 0.1)
+    assert len(seeds) == 103_823 and max_steps == 17
+    got, steps = M.topo_batch(seeds, n_iter, x, Q, 0.1, dims, want_steps=True)
+    assert np.all(steps >= 1) and np.all(steps <= n_iter)
+    assert np.all(got[:, 0] <= steps * 0.1 * (1 + 1e-5) + 1e-6)       # chord <= path length
+    assert np.all(np.isfinite(got)) and np.all(got[:, 1] >= 0)
+    c = M.last_counters()
+    assert c["field_evals"] == int(steps.astype(np.int64).sum() + 2 * len(steps))
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(len(seeds))
+    got_p = M.topo_batch(seeds[perm], n_iter[perm], x, Q, 0.1, dims)
+    np.testing.assert_array_equal(got_p, got[perm])                     # bit-exact, order-free
+    idx = rng.choice(len(seeds), 1500, replace=False)
+    want, wsteps = f64.topo_batch(seeds[idx], n_iter[idx], x, Q, 0.1, dims)
+    check_lines(got[idx], steps[idx], want, wsteps, 0.1, curv_tol_dir(0.1))
+
+
+# ------------------------------------------------------------------------------------ K3 --------
+def test_hist2d_bit_exact(M):
+    rng = np.random.default_rng(0)
+    d = rng.gamma(2.0, 0.3, 100_003).astype(np.float32)
+    c = rng.gamma(1.5, 0.4, 100_003).astype(np.float32)
+    v32 = np.column_stack([d, c])
+    v64 = v32.astype(np.float64)
+    for nd, nc, dr, cr in [(50, 50, (0.0, float(d.max())), (0.0, float(c.max()))),
+                           (37, 91, (float(d.min()), float(d.max())), (float(c.min()), float(c.max()))),
+                           (8, 5, (0.2, 0.9), (0.1, 2.0)),
+                           (300, 400, (0.0, 3.0), (0.0, 4.0))]:            # 120k bins: global-atomic path
+        de, ce = np.linspace(dr[0], dr[1], nd + 1), np.linspace(cr[0], cr[1], nc + 1)
+        want, _, _ = np.histogram2d(v64[:, 0], v64[:, 1], bins=[nd, nc], range=[dr, cr])
+        for vals in (v64, v32):
+            got = M.hist2d(vals, de, ce)
+            assert got.dtype == np.int64 and got.shape == (nd, nc)
+            np.testing.assert_array_equal(got, want.astype(np.int64))
+        np.testing.assert_array_equal(ohist.hist2d_counts(v64[:, 0], v64[:, 1], nd, nc, dr, cr),
+                                      want.astype(np.int64))
+
+
+def test_hist2d_edges_nan_batch(M):
+    ed = np.linspace(0.0, 1.0, 11)
+    dd = np.concatenate([ed, ed, [np.nan, -1.0, 2.0, 0.5]])
+    cc = np.concatenate([ed, ed[::-1], [0.5, 0.5, 0.5, np.nan]])
+    want, _, _ = np.histogram2d(dd[:22], cc[:22], bins=[10, 10], range=[(0, 1), (0, 1)])
+    got = M.hist2d(np.column_stack([dd, cc]), ed, ed)
+    np.testing.assert_array_equal(got, want.astype(np.int64))          # NaN / outliers dropped
+    # batched frames
+    rng = np.random.default_rng(3)
+    v = rng.random((5, 4001, 2))
+    got = M.hist2d(v, np.linspace(0, 1, 21), np.linspace(0, 1, 14))
+    for f in range(5):
+        w, _, _ = np.histogram2d(v[f, :, 0], v[f, :, 1], bins=[20, 13], range=[(0, 1), (0, 1)])
+        np.testing.assert_array_equal(got[f], w.astype(np.int64))
+    assert got.sum() == 5 * 4001
+    # empty input
+    assert M.hist2d(np.zeros((0, 2)), ed, ed).sum() == 0
+
+
+def test_make_histograms_and_chi2(M, tmp_path):
+    from pycpet_b200 import calculator as calc
+
+    rng = np.random.default_rng(9)
+    tops = [np.column_stack([rng.gamma(2.0 + 0.2 * i, 0.3, 5832), rng.gamma(1.5, 0.4, 5832)]).astype(np.float32)
+            for i in range(4)]
+    files = []
+    for i, t in enumerate(tops):
+        p = tmp_path / f"f{i}.top"
+        np.savetxt(p, t)                                  # what CPET.run_topo writes (CPET.py:123)
+        files.append(str(p))
+    H = calc.make_histograms(files)
+    # the reference's make_histograms, restated: global range, IQR bin width, np.histogram2d
+    allv = np.concatenate(tops).astype(np.float64)
+    dr, cr, nd, nc = ohist.bin_plan(allv[:, 0], allv[:, 1], 5832)
+    want = np.stack([ohist.normalised_hist(t[:, 0].astype(np.float64), t[:, 1].astype(np.float64), nd, nc, dr, cr)
+                     for t in tops])
+    np.testing.assert_array_equal(H, want)
+    D = calc.construct_distance_matrix(H)
+    Dw = ohist.chi2_matrix(want)
+    np.testing.assert_allclose(D, Dw, rtol=1e-12, atol=1e-15)
+    assert np.all(np.diag(D) == 0) and np.allclose(D, D.T, rtol=0, atol=0)
+    assert abs(calc.distance_numpy(H[0], H[1]) - ohist.chi2(want[0], want[1])) < 1e-14
+
+
+# --------------------------------------------------------------------------- legacy symbols -----
+def test_legacy_symbols(M, golden):
+    g = golden("synthetic_math_ops.npz")
+    x, Q, pts = g["x"], g["Q"], g["points"]
+    want = f64.field_grid(pts[:4], x, Q, False)
+    for i in range(4):
+        assert relmax(M.calc_field(pts[i], x, Q), want[i]) < FIELD_TOL
+        assert relmax(M.calc_field_base(pts[i], x, Q), want[i]) < FIELD_TOL
+        assert abs(M.calc_esp_base(pts[i], x, Q)[0] - f64.esp_grid(pts[i:i + 1], x, Q)[0]) < 1e-5 * 5
+    # accumulate-into-output quirk of calc_field_base / calc_esp_base (C:327-332, 482-485)
+    acc = np.array([1.0, 2.0, 3.0], dtype=np.float32)
+    M.math.calc_field_base(acc, pts[0], len(Q), x, Q)
+    np.testing.assert_allclose(acc - np.array([1, 2, 3], np.float32), want[0], rtol=1e-4, atol=1e-5)
+    esp = np.array([10.0], dtype=np.float32)
+    M.math.calc_esp_base(esp, pts[0], len(Q), x, Q)
+    assert abs((esp[0] - 10.0) - f64.esp_grid(pts[:1], x, Q)[0]) < 1e-4
+    # helper einsum symbols
+    rng = np.random.default_rng(0)
+    A = rng.random((50, 3)).astype(np.float32)
+    np.testing.assert_allclose(M.einsum_ij_i(A), A.sum(1), rtol=1e-6)
+    R = rng.normal(size=(40, 3)).astype(np.float32)
+    rm = rng.random(40).astype(np.float32)
+    q = rng.normal(size=40).astype(np.float32)
+    want_e = 14.3996451 * np.einsum("i,i,ij->j", q.astype(np.float64), rm.astype(np.float64), R.astype(np.float64))
+    np.testing.assert_allclose(M.einsum_operation(R, rm, q), want_e, rtol=1e-5)
+    Rb = rng.normal(size=(3, 40, 3)).astype(np.float32)
+    rmb = rng.random((3, 40)).astype(np.float32)
+    want_b = 14.3996451 * np.einsum("i,bi,bij->bj", q.astype(np.float64), rmb.astype(np.float64), Rb.astype(np.float64))
+    np.testing.assert_allclose(M.einsum_operation_batch(Rb, rmb, q, 3), want_b, rtol=1e-5)
+    a, b = rng.random(100).astype(np.float32), rng.random(100).astype(np.float32)
+    np.testing.assert_array_equal(M.vecaddn(a, b), a + b)
+    Ad, Bd = rng.random((7, 9)), rng.random(9)
+    np.testing.assert_allclose(M.dot(Ad, Bd), Ad @ Bd, rtol=1e-14)
+    import scipy.sparse as sp
+    S = sp.random(20, 9, density=0.3, format="csr", random_state=1)
+    np.testing.assert_allclose(M.sparse_dot(S, Bd), S @ Bd, rtol=1e-14)
+
+
+def test_dipole_tracer_symbol(M):
+    """thread_operation_dipole (development-only in the reference, C:593-660): checked against a
+    NumPy transcription of the same expression."""
+    rng = np.random.default_rng(4)
+    x = rng.uniform(-8, 8, (300, 3)).astype(np.float32)
+    x = x[np.linalg.norm(x, axis=1) > 2.0]
+    mu = rng.normal(size=(len(x), 3)).astype(np.float32)
+    dims = np.array([1, 1, 1], np.float32)
+    seed = np.array([0.1, -0.2, 0.3], np.float32)
+
+    def field(p):
+        R = p[None, :].astype(np.float64) - x
+        rn = np.linalg.norm(R, axis=1)
+        proj = 3 * mu[:, 0] * R[:, 0] + mu[:, 1] * R[:, 1] + mu[:, 2] * R[:, 2]
+        return (14.3996451 * rn[:, None] ** -5 * (proj[:, None] * R - mu * rn[:, None] ** 2)).sum(0)
+
+    def step(p):
+        e = field(p)
+        return p + 0.1 * e / np.linalg.norm(e)
+
+    p = seed.astype(np.float64)
+    for _ in range(5):
+        p = step(p)
+        if np.any(np.abs(p) > 1):
+            break
+    got = M.thread_operation_dipole(seed, 5, x, mu, 0.1, dims)
+    assert abs(got[0] - np.linalg.norm(p - seed)) < 1e-5
+
+
+def test_calculator_level_entry_points(golden, frame2a):
+    import types
+
+    import pycpet_b200 as pc
+
+    g = golden("example_2A_volume.npz")
+    t = golden("example_3A_topo.npz")
+    x, Q = frame2a
+    calc = types.SimpleNamespace(x=x, Q=Q.reshape(-1, 1), mesh=g["mesh"], dimensions=t["dimensions"],
+                                 step_size=float(t["step_size"]), random_start_points=t["seeds"],
+                                 random_max_samples=t["n_iter"], n_samples=216)
+    fb, shape = pc.compute_box(calc)
+    assert shape == (11, 11, 11, 3) and fb.shape == (1331, 6) and fb.dtype == np.float32
+    assert relmax(fb[:, 3:], g["field_box"][:, 3:]) < FIELD_TOL
+    eb, shape = pc.compute_box_ESP(calc)
+    assert eb.dtype == np.float16 and eb.shape == (1331, 4)
+    hist = pc.compute_topo_complete_c_shared(calc)
+    assert hist.shape == (216, 2) and calc.hist is hist
+    assert np.max(np.abs(hist[:, 0] - t["hist"][:, 0])) <= 2e-6
+    hist_gpu = pc.compute_topo_GPU_batch_filter(calc)
+    np.testing.assert_array_equal(hist_gpu, hist)
+    golden1 = golden("example_1A_point_field.npz")
+    c1 = types.SimpleNamespace(x=golden1["x"], Q=golden1["Q"])
+    np.testing.assert_allclose(pc.compute_point_field(c1), golden1["field"], rtol=2e-5)
+
+
+def test_engine_device_pointers_match_host_path(M, frame2a):
+    import torch
+
+    from pycpet_b200.device import Engine
+
+    x, Q = frame2a
+    eng = Engine(0)
+    eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
+    pts = synth.grid(11, 0.5)
+    e_dev = eng.field_grid(torch.from_numpy(pts).cuda(), soften=True, concat=True)
+    np.testing.assert_array_equal(e_dev.cpu().numpy(), M.field_grid(pts, x, Q, soften=True, concat=True))
+    seeds, n_iter, dims, _ = synth.seeds(12, 0.5, 0.1)
+    t_dev, s_dev = eng.topo_batch(torch.from_numpy(seeds).cuda(), n_iter, 0.1, dims, want_steps=True)
+    t_host, s_host = M.topo_batch(seeds, n_iter, x, Q, 0.1, dims, want_steps=True)
+    np.testing.assert_array_equal(t_dev.cpu().numpy(), t_host)
+    np.testing.assert_array_equal(s_dev.cpu().numpy(), s_host)
+    de, ce = np.linspace(0, 1.8, 31), np.linspace(0, 3.0, 41)
+    h_dev = eng.hist2d(t_dev, de, ce)
+    np.testing.assert_array_equal(h_dev.cpu().numpy(), M.hist2d(t_host, de, ce))
+    assert eng.fp32_peak_tflops(packed=True, iters=512) > 10.0
+    eng.close()

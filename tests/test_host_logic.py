@@ -1,0 +1,37 @@
+"""CPU: host-side logic of the mirror (bin planning, .top parsing, partitioners)."""
+import numpy as np
+
+from oracle import hist as ohist
+from pycpet_b200 import calculator as calc
+from pycpet_b200 import sharding
+
+
+def test_bin_plan_matches_reference_rule(tmp_path):
+    rng = np.random.default_rng(5)
+    tops = [np.column_stack([rng.gamma(2.0, 0.3, 1000), rng.gamma(1.5, 0.4, 1000)]).astype(np.float32)
+            for _ in range(3)]
+    dr, cr, nd, nc = calc.bin_plan(tops)
+    allv = np.concatenate(tops).astype(np.float64)
+    dr2, cr2, nd2, nc2 = ohist.bin_plan(allv[:, 0], allv[:, 1], 1000)
+    assert (dr, cr, nd, nc) == (dr2, cr2, nd2, nc2)
+    # .top round trip: written like CPET.py:123 (np.savetxt default %.18e)
+    p = tmp_path / "a.top"
+    np.savetxt(p, tops[0])
+    back = calc.read_top_file(str(p))
+    np.testing.assert_array_equal(back, tops[0].astype(np.float64))
+
+
+def test_partitioners():
+    for n, size in [(10, 3), (1331, 8), (5, 8), (0, 2)]:
+        spans = [sharding.slab(n, r, size) for r in range(size)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(size - 1))
+        lens = [b - a for a, b in spans]
+        assert max(lens) - min(lens) <= 1
+    assert sharding.frames_for_rank(10, 1, 4) == [1, 5, 9]
+    n_iter = np.random.RandomState(0).randint(1, 17, 1000)
+    parts = [sharding.deal_lines(n_iter, r, 4) for r in range(4)]
+    allids = np.sort(np.concatenate(parts))
+    np.testing.assert_array_equal(allids, np.arange(1000))
+    work = [n_iter[p].sum() for p in parts]
+    assert max(work) / min(work) < 1.05

@@ -1,0 +1,74 @@
+"""CPU, gloo, world_size 2: the N>1 path (partition -> local compute -> gather / all-reduce).
+The local compute is the float64 oracle here (no GPU in this tier); on the GPU box the same
+functions run with Engine methods over NCCL (tests/test_gpu_parity.py, bench.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import synth
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, size, port, tmp):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    from oracle import f64, hist as ohist
+    from pycpet_b200 import sharding
+
+    x, Q = synth.charges(500, seed=1, box=0.5)
+    pts = synth.grid(5, 0.5)
+    seeds, n_iter, dims, _ = synth.seeds(4, 0.5, 0.1)
+
+    full_field = sharding.grid_sharded(lambda p: f64.field_grid(p, x, Q, True), pts).numpy()
+    full_topo = sharding.topo_sharded(lambda s, n: f64.topo_batch(s, n, x, Q, 0.1, dims)[0], seeds, n_iter).numpy()
+    # histogram of the lines held by this rank, reduced
+    ids = sharding.deal_lines(n_iter, rank, size)
+    ref_topo = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)[0]
+    lo_d, hi_d, lo_c, hi_c = sharding.global_ranges(ref_topo[ids])
+    de, ce = ohist.edges(lo_d, hi_d, 7), ohist.edges(lo_c, hi_c, 5)
+    counts = sharding.hist_sharded(
+        lambda v, a, b: ohist.hist2d_counts(v[:, 0], v[:, 1], 7, 5, (a[0], a[-1]), (b[0], b[-1])),
+        ref_topo[ids], de, ce).numpy()
+    frames = sharding.frames_sharded(lambda f: np.full((2, 3), float(f)), 5).numpy()
+    np.savez(os.path.join(tmp, f"r{rank}.npz"), field=full_field, topo=full_topo, counts=counts,
+             frames=frames, ranges=np.array([lo_d, hi_d, lo_c, hi_c]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_gloo(tmp_path):
+    from oracle import f64, hist as ohist
+
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    x, Q = synth.charges(500, seed=1, box=0.5)
+    pts = synth.grid(5, 0.5)
+    seeds, n_iter, dims, _ = synth.seeds(4, 0.5, 0.1)
+    field = f64.field_grid(pts, x, Q, True)
+    topo = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)[0]
+    for r in range(2):
+        z = np.load(tmp_path / f"r{r}.npz")
+        np.testing.assert_array_equal(z["field"], field)
+        np.testing.assert_array_equal(z["topo"], topo)
+        rg = z["ranges"]
+        assert rg[0] == topo[:, 0].min() and rg[1] == topo[:, 0].max()
+        expect = ohist.hist2d_counts(topo[:, 0], topo[:, 1], 7, 5, (rg[0], rg[1]), (rg[2], rg[3]))
+        np.testing.assert_array_equal(z["counts"], expect)
+        assert z["counts"].sum() == len(topo)
+        np.testing.assert_array_equal(z["frames"][:, 0, 0], np.arange(5.0))
