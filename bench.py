@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract for the PyCPET hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A *step* = one pass of the hot path over one frame of synthetic input:
+upload/pack the frame's charges, run the kernel(s) of the workload, bin the result.  Default
+workload = BASELINE.json configs[1] ("3A_field-topology": 47^3 = 103,823 streamlines in a 0.5 A
+box, step 0.1, on a 7,890-charge protein-like frame, then the distance x curvature histogram).
+
+One JSON line on stdout (rank 0):
+  value      : whole-job pair-evaluations/s with inputs already resident in HBM (device-pointer
+               C-ABI), CUDA-event timed per step on the launching stream, L2 flushed between steps
+  e2e        : the same metric through the host-pointer C-ABI the reference-facing plugin calls
+               (pinned host buffers in, host buffers out; copies inside the timed region)
+  roofline   : the dominant kernel against the non-tensor FP32 issue rate (20 flop / pair-eval),
+               its duration measured live with CUDA events around that kernel alone
+  cpu_baseline: the reference's own C (oracle/_ref, compiled from /root/reference in place) on
+               this box's host cores, on a bounded sample of the same workload
+`--impl reference` times that CPU reference alone (rank 0 only) and prints the same line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FLOPS_PER_PAIR = 20.0            # BASELINE.json north_star: "counted at 20 flops/pair"
+ESP_FLOPS_PER_PAIR = 11.0
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.5: 148 SM x 128 lanes x 2 x 1.965 GHz
+
+WORKLOADS = {
+    # name: (kind, description, params)
+    "topo3a": ("topo", "3A_field-topology: topo, 47^3=103,823 streamlines, 7,890 synthetic protein-like "
+               "charges, box half-width 0.5 A, step 0.1 A (max_steps 17), + 2-D histogram",
+               dict(m=7890, n_axis=47, half=0.5, h=0.1)),
+    "md1m": ("topo", "MD-frame topology: 100^3=1,000,000 streamlines per frame, 7,890 charges, "
+             "box 0.5 A, step 0.1 A, + 2-D histogram", dict(m=7890, n_axis=100, half=0.5, h=0.1)),
+    "topo_fine": ("topo", "topo, 47^3 streamlines, 7,890 charges, box 0.5 A, step 0.01 A (max_steps 173)",
+                  dict(m=7890, n_axis=47, half=0.5, h=0.01)),
+    "volume2a": ("field", "2A_3D-field: volume E-field, 11^3 grid, 7,890 charges", dict(m=7890, n_axis=11, half=0.5)),
+    "volume": ("field", "synthetic sweep cell: volume E-field, 100^3 grid points x 100,000 charges",
+               dict(m=100_000, n_axis=100, half=1.5)),
+    "esp101": ("esp", "volume_ESP: 101^3 grid x ~100k-charge solvated system", dict(m=100_000, n_axis=101, half=5.0)),
+}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample NVML during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4, "hw_power_brake": 0x80}
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        self.samples, self.reasons = [], set()
+        self._stop.clear()
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None),
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+    def rejected(self):
+        if self.reasons & set(self.BAD):
+            return True
+        s = self.summary()
+        if s["sm_mhz"] and s["sm_max_mhz"] and s["sm_mhz"] < 0.6 * s["sm_max_mhz"] and not self.reasons:
+            return True       # stuck well below max with no reason: a leftover clock lock
+        return False
+
+
+# ------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------
+def make_inputs(kind, prm, frame_id):
+    """Synthetic frame `frame_id`: base charge set + per-frame Gaussian jitter sigma = 0.3 A
+    (seed = frame id), as SURVEY.md section 8(d) specifies for MD batches."""
+    import synth
+
+    x, Q = synth.charges(prm["m"], seed=1, box=prm["half"])
+    if frame_id > 0:
+        rng = np.random.default_rng(1000 + frame_id)
+        x = (x + rng.normal(0.0, 0.3, x.shape)).astype(np.float32)
+        inside = np.all(np.abs(x) < prm["half"] * 1.05, axis=1)
+        x[inside] *= np.float32(3.0)          # keep jittered charges out of the sampling box
+    d = dict(x=np.ascontiguousarray(x), Q=np.ascontiguousarray(Q))
+    if kind == "topo":
+        seeds, n_iter, dims, max_steps = synth.seeds(prm["n_axis"], prm["half"], prm["h"])
+        d.update(seeds=seeds, n_iter=n_iter.astype(np.int32), dims=dims, h=prm["h"], max_steps=max_steps)
+    else:
+        d.update(points=synth.grid(prm["n_axis"], prm["half"]))
+    return d
+
+
+def hist_edges(kind, prm):
+    # fixed-range variant (scripts/residue_breakdown_analysis.py:28-37 style): 50 x 50 bins
+    h = prm.get("h", 0.1)
+    n_max = round(2 * np.sqrt(3) * prm["half"] / h)
+    return np.linspace(0.0, n_max * h, 51), np.linspace(0.0, 5.0, 51)
+
+
+def pinned(a):
+    import torch
+
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t, t.numpy()
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from pycpet_b200 import Math_ops
+    from pycpet_b200.device import Engine
+
+    kind, desc, prm = WORKLOADS[args.workload]
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    inp = make_inputs(kind, prm, frame_id=rank)
+    de, ce = hist_edges(kind, prm)
+
+    # ---- device-resident arm ---------------------------------------------------------------
+    eng = Engine(local_rank)
+    eng.set_tuning(timing=1)
+    dx, dq = torch.from_numpy(inp["x"]).to(dev), torch.from_numpy(inp["Q"]).to(dev)
+    if kind == "topo":
+        dseeds, dnit = torch.from_numpy(inp["seeds"]).to(dev), torch.from_numpy(inp["n_iter"]).to(dev)
+        dout = torch.empty((len(inp["seeds"]), 2), dtype=torch.float32, device=dev)
+        dcounts = torch.empty((1, 50, 50), dtype=torch.int64, device=dev)
+    else:
+        dpts = torch.from_numpy(inp["points"]).to(dev)
+        n = len(inp["points"])
+        dout = (torch.empty((n, 6), dtype=torch.float32, device=dev) if kind == "field"
+                else torch.empty((n, 4), dtype=torch.float16, device=dev))
+    gathered = [torch.empty((1, 50, 50), dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    launches = {"n": 0}
+    kern_ms = []
+    work = {"pairs": 0, "units": 0}
+
+    def step_device(record=False):
+        eng.set_charges(dx, dq)                                          # pack kernel
+        n_launch = 1
+        if kind == "topo":
+            eng.topo_batch(dseeds, dnit, inp["h"], inp["dims"], out=dout)
+            if record:
+                kern_ms.append(eng.last_kernel_ms())                     # integrator kernel alone
+            c = eng.last_counters()
+            n_launch += c["launches"]
+            eng.hist2d(dout, de, ce, out=dcounts)
+            n_launch += 1
+            if world > 1:
+                dist.all_gather(gathered, dcounts)                       # the path's one exchange
+            work["pairs"], work["units"] = c["pair_evals"], len(inp["seeds"])
+        elif kind == "field":
+            eng.field_grid(dpts, soften=True, concat=True, out=dout)
+            if record:
+                kern_ms.append(eng.last_kernel_ms())
+            c = eng.last_counters()
+            n_launch += c["launches"]
+            work["pairs"], work["units"] = c["pair_evals"], len(inp["points"])
+        else:
+            eng.esp_grid(dpts, concat_half=True, out=dout)
+            if record:
+                kern_ms.append(eng.last_kernel_ms())
+            c = eng.last_counters()
+            n_launch += c["launches"]
+            work["pairs"], work["units"] = c["pair_evals"], len(inp["points"])
+        if record:
+            launches["n"] += n_launch
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+
+    def timed_device():
+        launches["n"] = 0
+        kern_ms.clear()
+        for _ in range(args.warmup):
+            flush_buf.zero_()
+            step_device()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        sampler.start()
+        for a, b in evs:
+            flush_buf.zero_()            # L2 flush, outside the per-step event bracket
+            a.record()
+            step_device(record=True)
+            b.record()
+        barrier()
+        sampler.stop()
+        return sum(a.elapsed_time(b) for a, b in evs) * 1e-3
+
+    t_dev = timed_device()
+    remeasured = False
+    if sampler.rejected():
+        remeasured = True
+        time.sleep(2.0)
+        t_dev = timed_device()
+    clocks = sampler.summary()
+    clocks["remeasured"] = remeasured
+
+    # ---- end-to-end arm: host-pointer C-ABI, pinned host buffers ---------------------------------
+    m = Math_ops(device=local_rank)
+    keep = []
+    def pin(a):
+        t, v = pinned(a)
+        keep.append(t)
+        return v
+    hx, hq = pin(inp["x"]), pin(inp["Q"])
+    if kind == "topo":
+        hseeds, hnit = pin(inp["seeds"]), pin(inp["n_iter"])
+        h2d = hx.nbytes + hq.nbytes + hseeds.nbytes + hnit.nbytes + len(hseeds) * 8 + de.nbytes + ce.nbytes
+        d2h = len(hseeds) * 8 + 50 * 50 * 8
+    else:
+        hpts = pin(inp["points"])
+        h2d = hx.nbytes + hq.nbytes + hpts.nbytes
+        d2h = len(hpts) * (24 if kind == "field" else 8)
+
+    def step_e2e():
+        m.set_charges(hx, hq)
+        if kind == "topo":
+            lines = m.topo_batch(hseeds, hnit, step_size=inp["h"], dimensions=inp["dims"])
+            return m.hist2d(lines, de, ce)
+        if kind == "field":
+            return m.field_grid(hpts, soften=True, concat=True)
+        return m.esp_grid(hpts, concat_half=True)
+
+    for _ in range(max(3, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+
+    # ---- reduce over ranks ---------------------------------------------------------------------------
+    tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    ww = torch.tensor([float(work["pairs"]), float(work["units"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+    t_dev, t_e2e = float(tt[0]), float(tt[1])
+    pairs_all, units_all = float(ww[0]), float(ww[1])
+
+    if rank != 0:
+        return None
+    flops = ESP_FLOPS_PER_PAIR if kind == "esp" else FLOPS_PER_PAIR
+    peak_ffma2 = eng.fp32_peak_tflops(True)
+    peak_ffma = eng.fp32_peak_tflops(False)
+    peak = max(peak_ffma2, peak_ffma)
+    k_ms = float(np.mean(kern_ms))
+    achieved = work["pairs"] * flops / (k_ms * 1e-3) / 1e12
+    value = pairs_all * args.steps / t_dev
+    line = {
+        "metric": "pair-evals/s", "value": value, "unit": "pair-evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": desc, "name": args.workload, "charges": int(len(inp["Q"])),
+                   "units_per_step_per_gpu": int(work["units"]),
+                   "pair_evals_per_step_per_gpu": int(work["pairs"]),
+                   "l2": "flushed between timed steps (256 MiB write)",
+                   "parallelism": f"frames sharded, 1 frame per GPU per step, x{world}"},
+        "units_per_s": units_all * args.steps / t_dev,
+        "units": "streamlines" if kind == "topo" else "grid points",
+        "fp32_frac_of_nominal": value / world * flops / 1e12 / NOMINAL_FP32_TFLOPS,
+        "clocks": clocks,
+        "e2e": {"value": pairs_all * args.steps / t_e2e, "unit": "pair-evals/s",
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches["n"]),
+        "roofline": {"bound": "fp32-non-tensor", "kernel": "k2_topo_kernel" if kind == "topo" else "k1_grid_kernel",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                     "peak_source": "measured live: register-resident FMA loop (cpet_fp32_peak_probe, "
+                                    f"FFMA2 {peak_ffma2:.1f} / FFMA {peak_ffma:.1f} TFLOP/s); "
+                                    "MEASURED_PEAKS.json has no FP32 entry",
+                     "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_nominal": achieved / NOMINAL_FP32_TFLOPS,
+                     "flops_per_pair": flops, "kernel_ms": k_ms, "traffic": None},
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline(kind, prm, inp, budget_s=args.cpu_seconds)
+    return line
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle/_ref = the reference's own math_module.c; oracle port otherwise)
+# ------------------------------------------------------------------------------------------------
+def cpu_run_sample(kind, inp, n_units, threads, use_ref):
+    from oracle import f64, ref
+
+    x, Q = inp["x"], inp["Q"]
+    if kind == "topo":
+        sel = np.linspace(0, len(inp["seeds"]) - 1, n_units).astype(np.int64)
+        seeds, n_iter = inp["seeds"][sel], inp["n_iter"][sel]
+        _, steps = f64.topo_batch(seeds, n_iter, x, Q, inp["h"], inp["dims"])       # work accounting only
+        credited = float((steps.astype(np.int64) + 2).sum()) * len(Q)
+        t0 = time.perf_counter()
+        if use_ref:
+            ref.topo(seeds, n_iter, x, Q, inp["h"], inp["dims"], threads=threads)
+        else:
+            f64.topo_batch(seeds, n_iter, x, Q, inp["h"], inp["dims"])
+        return time.perf_counter() - t0, credited
+    sel = np.linspace(0, len(inp["points"]) - 1, n_units).astype(np.int64)
+    pts = inp["points"][sel]
+    t0 = time.perf_counter()
+    if kind == "field":
+        ref.field_grid(pts, x, Q, threads=threads) if use_ref else f64.field_grid(pts, x, Q, True)
+    else:
+        ref.esp_grid(pts, x, Q, threads=threads) if use_ref else f64.esp_grid(pts, x, Q)
+    return time.perf_counter() - t0, float(len(pts)) * len(Q)
+
+
+def cpu_baseline(kind, prm, inp, budget_s=12.0, steps=1, warmup=0):
+    from oracle import f64, ref
+
+    use_ref = ref.available()
+    threads = os.cpu_count() or 1
+    if not use_ref:
+        threads = f64.num_threads()
+    total = len(inp["seeds"]) if kind == "topo" else len(inp["points"])
+    probe = min(total, 64 * threads)
+    t, w = cpu_run_sample(kind, inp, probe, threads, use_ref)            # calibration (also warms up)
+    n = int(min(total, max(probe, probe * budget_s / max(t, 1e-6))))
+    for _ in range(warmup):
+        cpu_run_sample(kind, inp, n, threads, use_ref)
+    tt, ww = 0.0, 0.0
+    for _ in range(steps):
+        t, w = cpu_run_sample(kind, inp, n, threads, use_ref)
+        tt += t
+        ww += w
+    return {"value": ww / tt, "unit": "pair-evals/s", "cores": threads,
+            "kind": "reference" if use_ref else "port",
+            "sample": f"{n} of {total} {'streamlines' if kind == 'topo' else 'grid points'} of the same frame "
+                      f"(evenly strided), {tt:.1f} s; work credited as sum(K+2) x M like the GPU arm"
+                      if kind == "topo" else
+                      f"{n} of {total} grid points of the same frame (evenly strided), {tt:.1f} s",
+            "impl": ("oracle/_ref: reference CPET/utils/math_module.c compiled in place "
+                     f"({os.path.basename(ref.path())}), one call per streamline/slab across host threads"
+                     if use_ref else "oracle port (cpet_oracle.c, float64, OpenMP)"),
+            "ms_per_step": tt / steps * 1e3}
+
+
+def run_reference(args):
+    kind, desc, prm = WORKLOADS[args.workload]
+    inp = make_inputs(kind, prm, frame_id=0)
+    budget = max(2.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    cb = cpu_baseline(kind, prm, inp, budget_s=budget, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "pair-evals/s", "value": cb["value"], "unit": "pair-evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "name": args.workload, "charges": int(len(inp["Q"]))},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "pair-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="topo3a", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps(run_reference(args)), flush=True)
+        return 0
+
+    args.warmup = max(args.warmup, 3)
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        line = run_gpu(args, rank, world, local_rank)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

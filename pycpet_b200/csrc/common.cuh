@@ -53,9 +53,13 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
     return r;
 }
+// MUFU.RSQ.  The .ftz form is a single instruction; without it ptxas wraps every rsqrt in a
+// denormal fix-up (FSETP + 2 predicated FMUL), which costs 3 extra issue slots per pair.  A
+// denormal r^2 (< 1.2e-38, i.e. r < 1e-19 A) is a coincident point/charge either way: flushed to
+// 0 it yields +inf, exactly what q*r^-3 overflows to in the reference's float arithmetic.
 __device__ __forceinline__ float rsqrt_approx(float x) {
     float r;
-    asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
@@ -150,6 +154,23 @@ __device__ __forceinline__ void eval_tile(const ChargePair* __restrict__ tile, i
         const PairA a = tile[j].a;
         const PairB b = tile[j].b;
         eval_pair<MODE, P>(a, b, r);
+    }
+}
+
+template <int MODE, int P>
+__device__ __forceinline__ void flush_partials(PointRegs<P>& r, double (&acc)[P][3]);
+
+// Same, but the FP32 partial sums are folded into the FP64 accumulators every CHUNK pairs per
+// lane, so no FP32 chain is longer than CHUNK additions (error ~ sqrt(CHUNK) * 2^-24 of the
+// running partial sum; matters for the heavily cancelling ESP sum of a neutral system).
+template <int MODE, int P, int UNROLL, int CHUNK>
+__device__ __forceinline__ void eval_tile_chunked(const ChargePair* __restrict__ tile, int first,
+                                                  int n, int stride, PointRegs<P>& r,
+                                                  double (&acc)[P][3]) {
+    for (int j0 = first; j0 < n; j0 += CHUNK * stride) {
+        const int j1 = min(n, j0 + CHUNK * stride);
+        eval_tile<MODE, P, UNROLL>(tile, j0, j1, stride, r);
+        flush_partials<MODE, P>(r, acc);
     }
 }
 

@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(256) k1_grid_kernel(const K1Params prm) {
         const int stage = t % S;
         mbar_wait(&full[stage], (uint32_t)((t / S) & 1));
         const int n_t = min(TP, npairs - t * TP);
-        eval_tile<MODE, P, (P >= 4 ? 2 : 4)>(ring + (size_t)stage * TP, lane_g, n_t, G, r);
-        flush_partials<MODE, P>(r, acc);
+        eval_tile_chunked<MODE, P, (P >= 4 ? 2 : 4), 128>(ring + (size_t)stage * TP, lane_g, n_t, G, r,
+                                                          acc);
         if (t + S < ntiles) {
             __syncthreads();           // every warp is done reading this stage
             if (tid == 0) issue(t + S);
@@ -264,7 +264,12 @@ int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, in
     if (G != 1 && G != 8 && G != 32) G = (G < 8) ? 8 : 32;
     int P = tu.k1_points;
     if (G > 1) P = 1;
-    else if (P <= 0) P = ((long long)n_points >= (long long)sms * 2048) ? 2 : 1;
+    else if (P <= 0) {
+        // measured (profiles/round1_sweep.md): E-field best at 4 points/thread, ESP (MUFU-bound) at 2
+        const long long n = n_points;
+        if (mode == MODE_ESP) P = (n >= (long long)sms * 2048) ? 2 : 1;
+        else P = (n >= (long long)sms * 4096) ? 4 : ((n >= (long long)sms * 2048) ? 2 : 1);
+    }
     if (P != 1 && P != 2 && P != 4) P = 2;
 
     const int pts_per_cta = (threads / G) * P;
@@ -286,10 +291,10 @@ int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, in
     if (pps < 8) pps = 8;
     splits = c->n_pairs > 0 ? (c->n_pairs + pps - 1) / pps : 1;
 
-    int tile_pairs = tu.k1_tile_pairs > 0 ? tu.k1_tile_pairs : 1024;
+    int tile_pairs = tu.k1_tile_pairs > 0 ? tu.k1_tile_pairs : (mode == MODE_ESP ? 512 : 1024);
     if (tile_pairs > pps) tile_pairs = pps;
     tile_pairs = ((tile_pairs + 7) / 8) * 8;
-    int stages = tu.k1_stages > 0 ? tu.k1_stages : 3;
+    int stages = tu.k1_stages > 0 ? tu.k1_stages : (mode == MODE_ESP ? 2 : 3);
     if (stages > 8) stages = 8;
     const int ntiles = (pps + tile_pairs - 1) / tile_pairs;
     if (stages > ntiles) stages = ntiles;

@@ -158,8 +158,7 @@ __global__ void __launch_bounds__(512, 1) k2_topo_kernel(const K2Params prm) {
         if (prm.resident) {
             for (int t = 0; t < NT; ++t) {
                 const int n_t = min(TP, prm.n_pairs - t * TP);
-                eval_tile<MODE_FIELD_RAW, 1, 4>(ring + (size_t)t * TP, lane_g, n_t, G, r);
-                flush_partials<MODE_FIELD_RAW, 1>(r, acc);
+                eval_tile_chunked<MODE_FIELD_RAW, 1, 4, 128>(ring + (size_t)t * TP, lane_g, n_t, G, r, acc);
             }
         } else {
             const bool warp_on = __any_sync(0xffffffffu, active);
@@ -168,8 +167,8 @@ __global__ void __launch_bounds__(512, 1) k2_topo_kernel(const K2Params prm) {
                 mbar_wait(&full[stage], (uint32_t)((it / S) & 1));
                 if (warp_on) {
                     const int n_t = min(TP, prm.n_pairs - t * TP);
-                    eval_tile<MODE_FIELD_RAW, 1, 4>(ring + (size_t)stage * TP, lane_g, n_t, G, r);
-                    flush_partials<MODE_FIELD_RAW, 1>(r, acc);
+                    eval_tile_chunked<MODE_FIELD_RAW, 1, 4, 128>(ring + (size_t)stage * TP, lane_g, n_t, G,
+                                                                 r, acc);
                 }
                 __syncthreads();                      // stage fully consumed by the CTA
                 if (tid == 0) { issue(issued); ++issued; }   // speculative: next round's tiles too
@@ -349,12 +348,10 @@ int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d
     if (threads > 512) threads = 512;
     int G = tu.k2_lanes;
     if (G <= 0) {
-        // aim for >= 4 lines per slot so the longest-first queue can even out the tail
+        // Measured on B200 (profiles/round1_sweep.md): 16 warps/SM are needed to hide latency, and
+        // the longest-first queue evens out the tail once there are >= ~2.5 lines per slot.
         G = 1;
-        while (G < 32 && (long long)n_lines * G < 4LL * sms * threads) G *= 2;
-        if (tu.k2_threads <= 0) {
-            while (threads > 128 && (long long)n_lines * G < 4LL * sms * threads) threads /= 2;
-        }
+        while (G < 32 && 2LL * n_lines * G < 5LL * sms * threads) G *= 2;
     }
     if (G & (G - 1)) G = 1;
     if (G > 32) G = 32;
@@ -375,7 +372,6 @@ int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d
     unsigned* cursor = offsets + K2_KEYMAX;
     prm.order = nullptr;
 
-    KernelTimer timer(c);
     if (do_sort) {
         if (int rc = c->work1.reserve(sizeof(int32_t) * (size_t)n_lines)) return rc;
         int blocks = (n_lines + 255) / 256;
@@ -398,6 +394,7 @@ int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d
     prm.out = d_out;
     prm.steps = d_steps;
 
+    KernelTimer timer(c);   // brackets the integrator kernel only (the roofline's "dominant kernel")
     int rc;
     switch (G) {
         case 1: rc = launch_k2_inst<1>(c, prm, grid, threads, smem); break;
