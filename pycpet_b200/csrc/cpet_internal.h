@@ -43,7 +43,7 @@ struct DevBuf {
 struct Tuning {
     int k1_threads = 0, k1_points = 0, k1_lanes = 0, k1_tile_pairs = 0, k1_stages = 0;
     int k1_splits = 0;
-    int k2_threads = 0, k2_lanes = 0, k2_tile_pairs = 0, k2_stages = 0, k2_ctas_per_sm = 0;
+    int k2_points = 0, k2_threads = 0, k2_lanes = 0, k2_tile_pairs = 0, k2_stages = 0, k2_ctas_per_sm = 0;
     int k2_sort = -1;   // -1 heuristic (on), 0 off, 1 on
     int timing = 0;
 };

@@ -62,7 +62,42 @@ __device__ __forceinline__ float curv3_f32(float3 a0, float3 a1, float3 a2) {
     return (float)((double)nc / d3);
 }
 
-template <int G>
+// 1/sqrt(a) and sqrt(a) in double from one MUFU.RSQ seed + two Newton steps (relative error
+// ~1e-15 after the second step) instead of the ~60-instruction software DSQRT/DDIV sequences: the
+// per-round state update is executed by every lane and sits on the critical path of each round.
+// Anything outside the comfortable float range (0, inf, NaN, denormal) takes the exact path, so the
+// reference's unguarded E/|E| semantics (NaN when E = 0, C:501) are unchanged.
+__device__ __forceinline__ double rsqrt_f64_fast(double a) {
+    const float af = (float)a;
+    if (af > 1e-30f && af < 1e30f) {
+        double y = (double)rsqrt_approx(af);
+        const double ha = 0.5 * a;
+        y = y * (1.5 - ha * y * y);
+        y = y * (1.5 - ha * y * y);
+        return y;
+    }
+    return 1.0 / sqrt(a);
+}
+__device__ __forceinline__ double sqrt_f64_fast(double a) {
+    const float af = (float)a;
+    if (af > 1e-30f && af < 1e30f) return a * rsqrt_f64_fast(a);
+    return sqrt(a);
+}
+
+// Per-streamline state, all in registers.  SD (second-difference curvature mode) additionally
+// keeps the two previous FP32 positions.
+template <bool SD>
+struct LineState {
+    int line, n_it, k, k_end;          // k = index of the current point; k_end = K once known
+    float px, py, pz;                  // current point p_k
+    float sx, sy, sz;                  // seed
+    float dist;                        // |seed - p_K|, fixed when K becomes known
+    double ux, uy, uz;                 // unit field direction at p_{k-1}
+    float kinit;                       // curvature at the seed end
+    float m1x, m1y, m1z, m2x, m2y, m2z;   // p_{k-1}, p_{k-2} (SD only)
+};
+
+template <int G, int P, bool SD>
 __global__ void __launch_bounds__(512, 1) k2_topo_kernel(const K2Params prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -100,22 +135,29 @@ __global__ void __launch_bounds__(512, 1) k2_topo_kernel(const K2Params prm) {
         for (int t = 0; t < NT; ++t) mbar_wait(&full[t], 0u);
     }
 
-    // ---- slot state --------------------------------------------------------------------------
-    bool active = false, exhausted = false;
-    int line = -1, n_it = 0, k = 0, k_end = -1;
-    float3 p = make_float3(0.f, 0.f, 0.f), pm1 = p, pm2 = p, s0 = p, pe = p;
-    double upx = 0.0, upy = 0.0, upz = 0.0;   // unit field direction at the previous point
-    float kinit_dir = 0.f, kinit_sd = 0.f;
+    // ---- slot state: P streamlines per thread (group of G lanes) -----------------------------
+    LineState<SD> st[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) {
+        st[q].line = -1; st[q].n_it = 0; st[q].k = 0; st[q].k_end = -1;
+        st[q].px = st[q].py = st[q].pz = 0.f;
+        st[q].sx = st[q].sy = st[q].sz = 0.f;
+        st[q].dist = 0.f; st[q].kinit = 0.f;
+        st[q].ux = st[q].uy = st[q].uz = 0.0;
+        st[q].m1x = st[q].m1y = st[q].m1z = st[q].m2x = st[q].m2y = st[q].m2z = 0.f;
+    }
+    bool exhausted = false;
     unsigned long long my_evals = 0ull;
     const double h = (double)prm.h;
     const double inv_h = 1.0 / h;
-    const bool second_diff = (prm.flags & CPET_TOPO_CURV_SECOND_DIFF) != 0u;
 
     int it = 0;   // consumed-tile counter (streamed mode)
     while (true) {
         // ---- refill empty slots from the queue (warp-aggregated atomic) ------------------------
-        {
-            const bool want = leader && !active && !exhausted;
+        bool any_active = false;
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            const bool want = leader && (st[q].line < 0) && !exhausted;
             const unsigned m = __ballot_sync(0xffffffffu, want);
             int slot = -1;
             if (m) {
@@ -128,103 +170,128 @@ __global__ void __launch_bounds__(512, 1) k2_topo_kernel(const K2Params prm) {
             if (G > 1) {
                 const int had = __shfl_sync(0xffffffffu, want ? 1 : 0, lane - lane_g);
                 const int sl = __shfl_sync(0xffffffffu, slot, lane - lane_g);
-                if (had) slot = sl; else slot = -1;
+                slot = had ? sl : -1;
             }
             if (slot >= 0) {
                 if (slot < prm.n_lines) {
-                    line = prm.order ? prm.order[slot] : slot;
-                    s0 = make_float3(prm.seeds[3 * (size_t)line], prm.seeds[3 * (size_t)line + 1],
-                                     prm.seeds[3 * (size_t)line + 2]);
-                    n_it = prm.n_iter[line];
-                    p = pm1 = pm2 = pe = s0;
-                    k = 0;
-                    k_end = (n_it <= 0) ? 0 : -1;
-                    active = true;
+                    const int line = prm.order ? prm.order[slot] : slot;
+                    st[q].line = line;
+                    st[q].sx = prm.seeds[3 * (size_t)line];
+                    st[q].sy = prm.seeds[3 * (size_t)line + 1];
+                    st[q].sz = prm.seeds[3 * (size_t)line + 2];
+                    st[q].n_it = prm.n_iter[line];
+                    st[q].px = st[q].sx; st[q].py = st[q].sy; st[q].pz = st[q].sz;
+                    if (SD) {
+                        st[q].m1x = st[q].m2x = st[q].sx; st[q].m1y = st[q].m2y = st[q].sy;
+                        st[q].m1z = st[q].m2z = st[q].sz;
+                    }
+                    st[q].k = 0;
+                    st[q].k_end = (st[q].n_it <= 0) ? 0 : -1;
+                    st[q].dist = 0.f;
                 } else {
                     exhausted = true;
                 }
             }
+            any_active = any_active || (st[q].line >= 0);
         }
         bool go;
-        if (prm.resident) go = __any_sync(0xffffffffu, active);
-        else go = __syncthreads_or(active ? 1 : 0) != 0;
+        if (prm.resident) go = __any_sync(0xffffffffu, any_active);
+        else go = __syncthreads_or(any_active ? 1 : 0) != 0;
         if (!go) break;
 
-        // ---- field at p: all charges --------------------------------------------------------
-        PointRegs<1> r;
-        set_point<1>(r, 0, p.x, p.y, p.z);
-        clear_partials<1>(r);
-        double acc[1][3] = {{0.0, 0.0, 0.0}};
+        // ---- field at the P current points: all charges ------------------------------------------
+        PointRegs<P> r;
+        double acc[P][3];
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            set_point<P>(r, q, st[q].px, st[q].py, st[q].pz);
+            acc[q][0] = acc[q][1] = acc[q][2] = 0.0;
+        }
+        clear_partials<P>(r);
         if (prm.resident) {
             for (int t = 0; t < NT; ++t) {
                 const int n_t = min(TP, prm.n_pairs - t * TP);
-                eval_tile_chunked<MODE_FIELD_RAW, 1, 4, 128>(ring + (size_t)t * TP, lane_g, n_t, G, r, acc);
+                eval_tile_chunked<MODE_FIELD_RAW, P, (P >= 2 ? 2 : 4), 64>(ring + (size_t)t * TP, lane_g,
+                                                                           n_t, G, r, acc);
             }
         } else {
-            const bool warp_on = __any_sync(0xffffffffu, active);
+            const bool warp_on = __any_sync(0xffffffffu, any_active);
             for (int t = 0; t < NT; ++t, ++it) {
                 const int stage = it % S;
                 mbar_wait(&full[stage], (uint32_t)((it / S) & 1));
                 if (warp_on) {
                     const int n_t = min(TP, prm.n_pairs - t * TP);
-                    eval_tile_chunked<MODE_FIELD_RAW, 1, 4, 128>(ring + (size_t)stage * TP, lane_g, n_t, G,
-                                                                 r, acc);
+                    eval_tile_chunked<MODE_FIELD_RAW, P, (P >= 2 ? 2 : 4), 64>(
+                        ring + (size_t)stage * TP, lane_g, n_t, G, r, acc);
                 }
                 __syncthreads();                      // stage fully consumed by the CTA
                 if (tid == 0) { issue(issued); ++issued; }   // speculative: next round's tiles too
             }
         }
-        double ex = acc[0][0], ey = acc[0][1], ez = acc[0][2];
-        if (G > 1) {
-#pragma unroll
-            for (int m = G / 2; m >= 1; m >>= 1) {
-                ex += shfl_xor_f64(ex, m);
-                ey += shfl_xor_f64(ey, m);
-                ez += shfl_xor_f64(ez, m);
-            }
-        }
 
-        // ---- per-slot state machine ----------------------------------------------------------
-        if (active) {
-            // unit direction (no zero guard: E = 0 gives NaN exactly like C:501)
-            const double inv_n = 1.0 / sqrt(ex * ex + ey * ey + ez * ez);
-            const double ux = ex * inv_n, uy = ey * inv_n, uz = ez * inv_n;
-            float kdir = 0.f;
-            if (k >= 1) {
-                const double cx = upy * uz - upz * uy;
-                const double cy = upz * ux - upx * uz;
-                const double cz = upx * uy - upy * ux;
-                kdir = (float)(sqrt(cx * cx + cy * cy + cz * cz) * inv_h);
+        // ---- per-slot state machines ----------------------------------------------------------------
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            double ex = acc[q][0], ey = acc[q][1], ez = acc[q][2];
+            if (G > 1) {
+#pragma unroll
+                for (int m = G / 2; m >= 1; m >>= 1) {
+                    ex += shfl_xor_f64(ex, m);
+                    ey += shfl_xor_f64(ey, m);
+                    ez += shfl_xor_f64(ez, m);
+                }
             }
-            if (k == 1) kinit_dir = kdir;
-            const float3 pn = make_float3((float)((double)p.x + h * ux), (float)((double)p.y + h * uy),
-                                          (float)((double)p.z + h * uz));
-            const bool last = (k_end >= 0) && (k == k_end + 1);
+            LineState<SD>& L = st[q];
+            if (L.line < 0) continue;
+            // unit direction (no zero guard: E = 0 gives NaN exactly like C:501)
+            const double inv_n = rsqrt_f64_fast(ex * ex + ey * ey + ez * ez);
+            const double ux = ex * inv_n, uy = ey * inv_n, uz = ez * inv_n;
+            const bool last = (L.k_end >= 0) && (L.k == L.k_end + 1);
+            float kdir = 0.f;
+            if (!SD && (L.k == 1 || last)) {   // curvature is needed at the first and last point pair
+                const double cx = L.uy * uz - L.uz * uy;
+                const double cy = L.uz * ux - L.ux * uz;
+                const double cz = L.ux * uy - L.uy * ux;
+                kdir = (float)(sqrt_f64_fast(cx * cx + cy * cy + cz * cz) * inv_h);
+                if (L.k == 1) L.kinit = kdir;
+            }
+            const float nx = (float)((double)L.px + h * ux);
+            const float ny = (float)((double)L.py + h * uy);
+            const float nz = (float)((double)L.pz + h * uz);
             if (last) {
-                const float kfin_sd = curv3_f32(pm1, p, pn);
-                if (k == 1) kinit_sd = kfin_sd;
+                if (SD) {
+                    kdir = curv3_f32(make_float3(L.m1x, L.m1y, L.m1z), make_float3(L.px, L.py, L.pz),
+                                     make_float3(nx, ny, nz));
+                    if (L.k == 1) L.kinit = kdir;
+                }
                 if (leader) {
-                    const double ddx = (double)s0.x - (double)pe.x;
-                    const double ddy = (double)s0.y - (double)pe.y;
-                    const double ddz = (double)s0.z - (double)pe.z;
-                    const float dist = (float)sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
-                    const float curv = second_diff ? (kinit_sd + kfin_sd) * 0.5f
-                                                   : (kinit_dir + kdir) * 0.5f;
-                    reinterpret_cast<float2*>(prm.out)[line] = make_float2(dist, curv);
-                    if (prm.steps) prm.steps[line] = k_end;
-                    my_evals += (unsigned long long)(k_end + 2);
+                    reinterpret_cast<float2*>(prm.out)[L.line] = make_float2(L.dist, (L.kinit + kdir) * 0.5f);
+                    if (prm.steps) prm.steps[L.line] = L.k_end;
+                    my_evals += (unsigned long long)(L.k_end + 2);
                 }
-                active = false;
+                L.line = -1;
             } else {
-                pm2 = pm1; pm1 = p; p = pn;
-                ++k;
-                if (k == 2) kinit_sd = curv3_f32(pm2, pm1, p);
-                if (k_end < 0) {
-                    const bool outside = (p.x < -prm.dimx) || (p.x > prm.dimx) || (p.y < -prm.dimy) ||
-                                         (p.y > prm.dimy) || (p.z < -prm.dimz) || (p.z > prm.dimz);
-                    if (k >= n_it || outside) { k_end = k; pe = p; }
+                if (SD) {
+                    L.m2x = L.m1x; L.m2y = L.m1y; L.m2z = L.m1z;
+                    L.m1x = L.px; L.m1y = L.py; L.m1z = L.pz;
                 }
-                upx = ux; upy = uy; upz = uz;
+                L.px = nx; L.py = ny; L.pz = nz;
+                ++L.k;
+                if (SD && L.k == 2)
+                    L.kinit = curv3_f32(make_float3(L.m2x, L.m2y, L.m2z), make_float3(L.m1x, L.m1y, L.m1z),
+                                        make_float3(nx, ny, nz));
+                if (L.k_end < 0) {
+                    const bool outside = (nx < -prm.dimx) || (nx > prm.dimx) || (ny < -prm.dimy) ||
+                                         (ny > prm.dimy) || (nz < -prm.dimz) || (nz > prm.dimz);
+                    if (L.k >= L.n_it || outside) {
+                        L.k_end = L.k;
+                        const double ddx = (double)L.sx - (double)nx;
+                        const double ddy = (double)L.sy - (double)ny;
+                        const double ddz = (double)L.sz - (double)nz;
+                        L.dist = (float)sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+                    }
+                }
+                L.ux = ux; L.uy = uy; L.uz = uz;
             }
         }
     }
@@ -293,9 +360,9 @@ __global__ void __launch_bounds__(256) k2_scatter_kernel(const int32_t* __restri
     }
 }
 
-template <int G>
+template <int G, int P, bool SD>
 static int launch_k2_inst(cpet_ctx* c, const K2Params& prm, int grid, int threads, size_t smem) {
-    auto kern = k2_topo_kernel<G>;
+    auto kern = k2_topo_kernel<G, P, SD>;
     CPET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, c->stream>>>(prm);
     CPET_CUDA_TRY(cudaGetLastError());
@@ -346,17 +413,19 @@ int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d
     threads = (threads / 32) * 32;
     if (threads < 32) threads = 32;
     if (threads > 512) threads = 512;
+    int P = tu.k2_points;
+    if (P != 1 && P != 2) P = 1;
     int G = tu.k2_lanes;
     if (G <= 0) {
         // Measured on B200 (profiles/round1_sweep.md): 16 warps/SM are needed to hide latency, and
         // the longest-first queue evens out the tail once there are >= ~2.5 lines per slot.
         G = 1;
-        while (G < 32 && 2LL * n_lines * G < 5LL * sms * threads) G *= 2;
+        while (G < 32 && 2LL * n_lines * G < 5LL * sms * threads * P) G *= 2;
     }
     if (G & (G - 1)) G = 1;
     if (G > 32) G = 32;
     int grid = sms;
-    const long long slots_per_cta = threads / G;
+    const long long slots_per_cta = (long long)(threads / G) * P;
     const long long need_ctas = (n_lines + slots_per_cta - 1) / slots_per_cta;
     if (need_ctas < grid) grid = (int)need_ctas;
 
@@ -396,14 +465,20 @@ int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d
 
     KernelTimer timer(c);   // brackets the integrator kernel only (the roofline's "dominant kernel")
     int rc;
+    const bool sd = (flags & CPET_TOPO_CURV_SECOND_DIFF) != 0u;
+#define CPET_K2_CASE(GG)                                                                         \
+    case GG:                                                                                     \
+        if (sd) rc = (P == 2) ? launch_k2_inst<GG, 2, true>(c, prm, grid, threads, smem)          \
+                              : launch_k2_inst<GG, 1, true>(c, prm, grid, threads, smem);         \
+        else rc = (P == 2) ? launch_k2_inst<GG, 2, false>(c, prm, grid, threads, smem)            \
+                           : launch_k2_inst<GG, 1, false>(c, prm, grid, threads, smem);           \
+        break;
     switch (G) {
-        case 1: rc = launch_k2_inst<1>(c, prm, grid, threads, smem); break;
-        case 2: rc = launch_k2_inst<2>(c, prm, grid, threads, smem); break;
-        case 4: rc = launch_k2_inst<4>(c, prm, grid, threads, smem); break;
-        case 8: rc = launch_k2_inst<8>(c, prm, grid, threads, smem); break;
-        case 16: rc = launch_k2_inst<16>(c, prm, grid, threads, smem); break;
-        default: rc = launch_k2_inst<32>(c, prm, grid, threads, smem); break;
+        CPET_K2_CASE(1) CPET_K2_CASE(2) CPET_K2_CASE(4) CPET_K2_CASE(8) CPET_K2_CASE(16)
+        default:
+        CPET_K2_CASE(32)
     }
+#undef CPET_K2_CASE
     if (rc) return rc;
     launches += 1;
     c->last_counters[0] = launches;
