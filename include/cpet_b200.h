@@ -58,6 +58,8 @@ int cpet_create_on_stream(int device, void *cuda_stream, cpet_ctx **out);
 int cpet_destroy(cpet_ctx *ctx);
 int cpet_sync(cpet_ctx *ctx);
 int cpet_device_of(cpet_ctx *ctx);
+/* Diagnostic: which K1 kernel served the last field/ESP call (0 general, 1 lattice). */
+int cpet_last_path(cpet_ctx *ctx);
 /* Tuning knobs for experiments: key in {"k1_threads","k1_points","k1_lanes","k1_tile_pairs",
  * "k1_stages","k2_threads","k2_lanes","k2_tile_pairs","k2_stages","k2_ctas_per_sm","k2_sort"};
  * value <= 0 restores the built-in heuristic. */
@@ -90,6 +92,21 @@ int cpet_field_grid_dev(cpet_ctx *ctx, int n_points, const float *d_x0, unsigned
  * CPET_OUT_CONCAT (each value rounded f64->f32->f16 as the reference's casts do). */
 int cpet_esp_grid(cpet_ctx *ctx, int n_points, const float *x0, unsigned flags, void *out);
 int cpet_esp_grid_dev(cpet_ctx *ctx, int n_points, const float *d_x0, unsigned flags, void *d_out);
+
+/* The same two sums on a tensor-product lattice: point (i,j,k) = (xs[i], ys[j], zs[k]), flattened
+ * with k fastest -- exactly the mesh initialize_box_points_uniform builds (UC:218-233:
+ * linspace per axis, meshgrid(indexing="ij"), reshape(-1,3)) and compute_field_on_grid /
+ * compute_ESP_on_grid receive.  dx, dy and dx^2+dy^2 are shared along z, which removes a quarter of
+ * the FP32 instructions per pair; results are bit-identical to cpet_field_grid / cpet_esp_grid on
+ * the expanded point list.  Output layouts and flags as above (N = nx*ny*nz rows). */
+int cpet_field_lattice(cpet_ctx *ctx, int nx, int ny, int nz, const float *xs, const float *ys,
+                       const float *zs, unsigned flags, float *out);
+int cpet_field_lattice_dev(cpet_ctx *ctx, int nx, int ny, int nz, const float *d_xs,
+                           const float *d_ys, const float *d_zs, unsigned flags, float *d_out);
+int cpet_esp_lattice(cpet_ctx *ctx, int nx, int ny, int nz, const float *xs, const float *ys,
+                     const float *zs, unsigned flags, void *out);
+int cpet_esp_lattice_dev(cpet_ctx *ctx, int nx, int ny, int nz, const float *d_xs, const float *d_ys,
+                         const float *d_zs, unsigned flags, void *d_out);
 
 /* One streamline step for N independent points: out_i = p_i + h E(p_i)/|E(p_i)|, no zero guard
  * (propagate_topo, C:489-503; field without softening, C:296-333).  out: (N,3) f32. */
@@ -133,6 +150,15 @@ int cpet_hist2d_dev(cpet_ctx *ctx, int n_frames, int64_t n_per_frame, const floa
                     int nd, const double *d_edges_host, int nc, const double *c_edges_host,
                     int64_t *d_counts);
 
+/* One frame end to end: cpet_topo_batch followed by cpet_hist2d on its (L,2) rows WITHOUT the rows
+ * leaving the device in between (what run_topo + make_histograms do through a .top text file,
+ * TOP:96-127 + UC:596-718).  out_rows (L,2) f32 and steps (L,) i32 may each be NULL when only the
+ * histogram is wanted; counts is (nd,nc) int64. */
+int cpet_topo_hist(cpet_ctx *ctx, int n_lines, const float *seeds, const int32_t *n_iter,
+                   float step_size, const float dims[3], unsigned flags, float *out_rows,
+                   int32_t *steps, int nd, const double *d_edges, int nc, const double *c_edges,
+                   int64_t *counts);
+
 /* Pairwise chi^2 distance matrix (UC:975-978, UC:1003-1015):
  * out[i][j] = 1/2 sum_{b: h_i[b]+h_j[b] != 0} (h_i[b]-h_j[b])^2 / (h_i[b]+h_j[b]); diagonal 0.
  * H: (n_hists, n_bins) float64 host; out: (n_hists, n_hists) float64 host. */
@@ -145,6 +171,10 @@ int cpet_fp32_peak_probe(cpet_ctx *ctx, int packed, int iters, double *tflops);
 /* Time of the kernels of the last call as measured with CUDA events on the context's stream
  * (milliseconds; 0 if timing was not enabled with cpet_set_tuning(ctx,"timing",1)). */
 int cpet_last_kernel_ms(cpet_ctx *ctx, double *ms);
+/* Durations (ms) of the dominant-kernel launches recorded since the previous call of this function
+ * (up to 256, oldest first), without any synchronisation having happened in between; resets the
+ * record.  Needs cpet_set_tuning(ctx,"timing",1). */
+int cpet_kernel_times(cpet_ctx *ctx, double *ms, int max_n, int *n_out);
 
 /* ================================================================ (A) legacy symbols ======= */
 /* Same names / argument order as the reference's math_module.c so that OPS:8-159 binds them.

@@ -45,6 +45,7 @@ SIGNATURES = {
     "cpet_destroy": (c_int, [c_void_p]),
     "cpet_sync": (c_int, [c_void_p]),
     "cpet_device_of": (c_int, [c_void_p]),
+    "cpet_last_path": (c_int, [c_void_p]),
     "cpet_set_tuning": (c_int, [c_void_p, ctypes.c_char_p, c_int]),
     "cpet_last_counters": (c_int, [c_void_p, ctypes.POINTER(c_int64)]),
     "cpet_set_charges": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
@@ -53,6 +54,10 @@ SIGNATURES = {
     "cpet_field_grid_dev": (c_int, [c_void_p, c_int, c_void_p, c_uint, c_void_p]),
     "cpet_esp_grid": (c_int, [c_void_p, c_int, c_void_p, c_uint, c_void_p]),
     "cpet_esp_grid_dev": (c_int, [c_void_p, c_int, c_void_p, c_uint, c_void_p]),
+    "cpet_field_lattice": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_uint, c_void_p]),
+    "cpet_field_lattice_dev": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_uint, c_void_p]),
+    "cpet_esp_lattice": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_uint, c_void_p]),
+    "cpet_esp_lattice_dev": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_uint, c_void_p]),
     "cpet_propagate": (c_int, [c_void_p, c_int, c_void_p, c_float, c_void_p]),
     "cpet_propagate_dev": (c_int, [c_void_p, c_int, c_void_p, c_float, c_void_p]),
     "cpet_topo_batch": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_uint,
@@ -65,9 +70,12 @@ SIGNATURES = {
                                 c_void_p, c_void_p]),
     "cpet_hist2d_dev": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_void_p, c_int,
                                 c_void_p, c_void_p]),
+    "cpet_topo_hist": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_uint, c_void_p,
+                               c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "cpet_chi2_matrix": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "cpet_fp32_peak_probe": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(ctypes.c_double)]),
     "cpet_last_kernel_ms": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "cpet_kernel_times": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), c_int, ctypes.POINTER(c_int)]),
 }
 
 # the reference's own symbol names (include/cpet_b200.h section (A)); argtypes are set by Math_ops

@@ -103,6 +103,10 @@ class Math_ops:
         check(self.math.cpet_last_counters(self.ctx, out))
         return {"launches": int(out[0]), "pair_evals": int(out[1]), "field_evals": int(out[2])}
 
+    def last_path(self) -> str:
+        """Which K1 kernel served the last field/ESP call: 'lattice' or 'general'."""
+        return "lattice" if self.math.cpet_last_path(self.ctx) == 1 else "general"
+
     def last_kernel_ms(self) -> float:
         ms = ctypes.c_double(0.0)
         check(self.math.cpet_last_kernel_ms(self.ctx, ctypes.byref(ms)))
@@ -123,26 +127,59 @@ class Math_ops:
         check(self.math.cpet_set_charges(self.ctx, x.shape[0], ptr(x), ptr(Q)))
         return x.shape[0]
 
-    def field_grid(self, x_0, x=None, Q=None, soften=True, concat=False):
+    @staticmethod
+    def _out(out, shape, dtype):
+        """Caller-supplied output buffer (e.g. pinned host memory) or a fresh array."""
+        if out is None:
+            return np.zeros(shape, dtype=dtype)
+        if out.shape != tuple(shape) or out.dtype != np.dtype(dtype) or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"out must be a C-contiguous {np.dtype(dtype)} array of shape {tuple(shape)}")
+        return out
+
+    def field_grid(self, x_0, x=None, Q=None, soften=True, concat=False, out=None):
         """E at points x_0 (N,3) -> (N,3) float32, or (N,6) [x_0|E] with concat=True."""
         if x is not None:
             self.set_charges(x, Q)
         x_0 = f32c(x_0, (-1, 3))
         n = x_0.shape[0]
-        out = np.zeros((n, 6 if concat else 3), dtype=np.float32)
+        out = self._out(out, (n, 6 if concat else 3), np.float32)
         flags = (_lib.CPET_FIELD_SOFTEN if soften else 0) | (_lib.CPET_OUT_CONCAT if concat else 0)
         check(self.math.cpet_field_grid(self.ctx, n, ptr(x_0), flags, ptr(out)))
         return out
 
-    def esp_grid(self, x_0, x=None, Q=None, concat_half=False):
+    def esp_grid(self, x_0, x=None, Q=None, concat_half=False, out=None):
         """phi at points x_0 (N,3) -> (N,) float32, or (N,4) float16 [x_0|phi] with concat_half."""
         if x is not None:
             self.set_charges(x, Q)
         x_0 = f32c(x_0, (-1, 3))
         n = x_0.shape[0]
-        out = np.zeros((n, 4), dtype=np.float16) if concat_half else np.zeros(n, dtype=np.float32)
+        out = self._out(out, (n, 4), np.float16) if concat_half else self._out(out, (n,), np.float32)
         check(self.math.cpet_esp_grid(self.ctx, n, ptr(x_0), _lib.CPET_OUT_CONCAT if concat_half else 0,
                                       ptr(out)))
+        return out
+
+    def field_lattice(self, xs, ys, zs, x=None, Q=None, soften=True, concat=False, out=None):
+        """E on the tensor-product grid xs x ys x zs (z fastest) -> (nx*ny*nz, 3 or 6) float32;
+        bit-identical to field_grid on the expanded point list, ~25 % fewer instructions."""
+        if x is not None:
+            self.set_charges(x, Q)
+        xs, ys, zs = f32c(xs, (-1,)), f32c(ys, (-1,)), f32c(zs, (-1,))
+        n = xs.shape[0] * ys.shape[0] * zs.shape[0]
+        out = self._out(out, (n, 6 if concat else 3), np.float32)
+        flags = (_lib.CPET_FIELD_SOFTEN if soften else 0) | (_lib.CPET_OUT_CONCAT if concat else 0)
+        check(self.math.cpet_field_lattice(self.ctx, xs.shape[0], ys.shape[0], zs.shape[0], ptr(xs), ptr(ys),
+                                           ptr(zs), flags, ptr(out)))
+        return out
+
+    def esp_lattice(self, xs, ys, zs, x=None, Q=None, concat_half=False, out=None):
+        """phi on the tensor-product grid xs x ys x zs -> (N,) float32 or (N,4) float16."""
+        if x is not None:
+            self.set_charges(x, Q)
+        xs, ys, zs = f32c(xs, (-1,)), f32c(ys, (-1,)), f32c(zs, (-1,))
+        n = xs.shape[0] * ys.shape[0] * zs.shape[0]
+        out = self._out(out, (n, 4), np.float16) if concat_half else self._out(out, (n,), np.float32)
+        check(self.math.cpet_esp_lattice(self.ctx, xs.shape[0], ys.shape[0], zs.shape[0], ptr(xs), ptr(ys),
+                                         ptr(zs), _lib.CPET_OUT_CONCAT if concat_half else 0, ptr(out)))
         return out
 
     def propagate(self, x_0, step_size, x=None, Q=None):
@@ -155,7 +192,7 @@ class Math_ops:
         return out
 
     def topo_batch(self, seeds, n_iter, x=None, Q=None, step_size=0.1, dimensions=(1, 1, 1),
-                   second_diff=False, want_steps=False):
+                   second_diff=False, want_steps=False, out=None):
         """All streamlines of a frame -> (L,2) float32 [dist|curv] in seed order."""
         if x is not None:
             self.set_charges(x, Q)
@@ -165,13 +202,36 @@ class Math_ops:
         if n_iter.shape[0] != n:
             raise ValueError(f"{n} seeds but {n_iter.shape[0]} n_iter entries")
         dims = f32c(dimensions, (3,))
-        out = np.zeros((n, 2), dtype=np.float32)
+        out = self._out(out, (n, 2), np.float32)
         steps = np.zeros(n, dtype=np.int32) if want_steps else None
         check(self.math.cpet_topo_batch(
             self.ctx, n, ptr(seeds), ptr(n_iter), float(step_size), ptr(dims),
             _lib.CPET_TOPO_CURV_SECOND_DIFF if second_diff else 0, ptr(out),
             ptr(steps) if want_steps else None))
         return (out, steps) if want_steps else out
+
+    def topo_hist(self, seeds, n_iter, d_edges, c_edges, x=None, Q=None, step_size=0.1,
+                  dimensions=(1, 1, 1), second_diff=False, want_rows=True, out=None, counts_out=None):
+        """One frame end to end: streamlines, then their 2-D histogram, with the (L,2) rows staying
+        on the device in between.  -> (rows (L,2) float32 or None, counts (nd,nc) int64)."""
+        if x is not None:
+            self.set_charges(x, Q)
+        seeds = f32c(seeds, (-1, 3))
+        n = seeds.shape[0]
+        n_iter = np.ascontiguousarray(np.asarray(n_iter).reshape(-1), dtype=np.int32)
+        if n_iter.shape[0] != n:
+            raise ValueError(f"{n} seeds but {n_iter.shape[0]} n_iter entries")
+        dims = f32c(dimensions, (3,))
+        de = np.ascontiguousarray(d_edges, dtype=np.float64)
+        ce = np.ascontiguousarray(c_edges, dtype=np.float64)
+        nd, nc = de.shape[0] - 1, ce.shape[0] - 1
+        rows = self._out(out, (n, 2), np.float32) if want_rows else None
+        counts = self._out(counts_out, (nd, nc), np.int64)
+        check(self.math.cpet_topo_hist(
+            self.ctx, n, ptr(seeds), ptr(n_iter), float(step_size), ptr(dims),
+            _lib.CPET_TOPO_CURV_SECOND_DIFF if second_diff else 0,
+            ptr(rows) if want_rows else None, None, nd, ptr(de), nc, ptr(ce), ptr(counts)))
+        return rows, counts
 
     def hist2d(self, values, d_edges, c_edges):
         """Batched np.histogram2d counts.  values: (F, n, 2) or (n, 2), float64 or float32.

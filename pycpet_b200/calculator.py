@@ -37,9 +37,28 @@ def __getattr__(name):
 # ------------------------------------------------------------------------------------------------
 # free functions (CPET/utils/calculator.py)
 # ------------------------------------------------------------------------------------------------
+def lattice_axes(grid_coords):
+    """If grid_coords is the (nx,ny,nz,3) float32 tensor-product mesh that
+    initialize_box_points_uniform builds (UC:218-233: meshgrid(indexing="ij") of three coordinate
+    vectors, last axis fastest), return its axis vectors (xs, ys, zs); otherwise None.  The check is
+    exact (every node compared), so the lattice kernel sees precisely the points the general kernel
+    would."""
+    g = np.asarray(grid_coords)
+    if g.ndim != 4 or g.shape[3] != 3 or g.dtype != np.float32 or min(g.shape[:3]) < 1:
+        return None
+    xs, ys, zs = g[:, 0, 0, 0], g[0, :, 0, 1], g[0, 0, :, 2]
+    if not (np.array_equal(g[..., 0], np.broadcast_to(xs[:, None, None], g.shape[:3])) and
+            np.array_equal(g[..., 1], np.broadcast_to(ys[None, :, None], g.shape[:3])) and
+            np.array_equal(g[..., 2], np.broadcast_to(zs[None, None, :], g.shape[:3]))):
+        return None
+    return np.ascontiguousarray(xs), np.ascontiguousarray(ys), np.ascontiguousarray(zs)
+
+
 def compute_field_on_grid(grid_coords, x, Q):
     """UC:430-447.  grid_coords (..., 3) -> (N,6) float32 rows [point | E] with the `volume`
-    softening max(r^2, 1e-6); one kernel launch instead of one C loop."""
+    softening max(r^2, 1e-6); one kernel launch instead of one C loop.  The library recognises
+    box meshes in the flat point list on the device and gives them the lattice kernel (same
+    numbers, fewer instructions); anything else takes the general kernel."""
     x_0 = np.asarray(grid_coords).reshape(-1, 3)
     return get_math().field_grid(x_0, x, Q, soften=True, concat=True)
 

@@ -49,18 +49,33 @@ void DevBuf::release() {
     cap = 0;
 }
 
+static bool timer_slot(cpet_ctx* c, int i) {
+    if (!c->ev0[i]) {
+        if (cudaEventCreate(&c->ev0[i]) != cudaSuccess || cudaEventCreate(&c->ev1[i]) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+    }
+    return true;
+}
 KernelTimer::KernelTimer(cpet_ctx* ctx) : c(ctx) {
-    if (c->tune.timing && c->ev0) cudaEventRecord(c->ev0, c->stream);
+    if (!c->tune.timing) return;
+    const int i = c->timer_count % cpet_ctx::kTimerRing;
+    if (timer_slot(c, i)) cudaEventRecord(c->ev0[i], c->stream);
 }
 KernelTimer::~KernelTimer() {
-    if (c->tune.timing && c->ev1) cudaEventRecord(c->ev1, c->stream);
+    if (!c->tune.timing) return;
+    const int i = c->timer_count % cpet_ctx::kTimerRing;
+    if (c->ev1[i]) cudaEventRecord(c->ev1[i], c->stream);
+    ++c->timer_count;
 }
 
 static int resolve_timer(cpet_ctx* c) {
-    if (!c->tune.timing) { c->last_kernel_ms = 0.0; return CPET_OK; }
-    CPET_CUDA_TRY(cudaEventSynchronize(c->ev1));
+    if (!c->tune.timing || c->timer_count == 0) { c->last_kernel_ms = 0.0; return CPET_OK; }
+    const int i = (c->timer_count - 1) % cpet_ctx::kTimerRing;
+    CPET_CUDA_TRY(cudaEventSynchronize(c->ev1[i]));
     float ms = 0.f;
-    CPET_CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    CPET_CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0[i], c->ev1[i]));
     c->last_kernel_ms = ms;
     return CPET_OK;
 }
@@ -101,8 +116,6 @@ static int make_ctx(int device, void* stream, bool borrow, cpet_ctx** out) {
         }
         c->own_stream = true;
     }
-    cudaEventCreate(&c->ev0);
-    cudaEventCreate(&c->ev1);
     *out = c;
     return CPET_OK;
 }
@@ -151,8 +164,10 @@ int cpet_destroy(cpet_ctx* c) {
     c->charges.release(); c->raw_x.release(); c->raw_q.release();
     c->in0.release(); c->in1.release(); c->out0.release(); c->out1.release();
     c->work0.release(); c->work1.release(); c->work2.release(); c->counters.release();
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int i = 0; i < cpet_ctx::kTimerRing; ++i) {
+        if (c->ev0[i]) cudaEventDestroy(c->ev0[i]);
+        if (c->ev1[i]) cudaEventDestroy(c->ev1[i]);
+    }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return CPET_OK;
@@ -165,20 +180,21 @@ int cpet_sync(cpet_ctx* c) {
 }
 
 int cpet_device_of(cpet_ctx* c) { return c ? c->device : -1; }
+int cpet_last_path(cpet_ctx* c) { return c ? c->last_path : -1; }
 
 int cpet_set_tuning(cpet_ctx* c, const char* key, int value) {
     CPET_REQUIRE(c && key, CPET_ERR_INVALID, "cpet_set_tuning: NULL argument");
     Tuning& t = c->tune;
     struct { const char* k; int* v; } tab[] = {
         {"k1_threads", &t.k1_threads}, {"k1_points", &t.k1_points}, {"k1_lanes", &t.k1_lanes},
-        {"k1_tile_pairs", &t.k1_tile_pairs}, {"k1_stages", &t.k1_stages}, {"k1_splits", &t.k1_splits},
+        {"k1_tile_pairs", &t.k1_tile_pairs}, {"k1_stages", &t.k1_stages}, {"k1_splits", &t.k1_splits}, {"k1_lattice", &t.k1_lattice},
         {"k2_points", &t.k2_points}, {"k2_threads", &t.k2_threads}, {"k2_lanes", &t.k2_lanes}, {"k2_tile_pairs", &t.k2_tile_pairs},
         {"k2_stages", &t.k2_stages}, {"k2_ctas_per_sm", &t.k2_ctas_per_sm}, {"k2_sort", &t.k2_sort},
         {"timing", &t.timing},
     };
     for (auto& e : tab) {
         if (strcmp(e.k, key) == 0) {
-            if (e.v == &t.k2_sort) *e.v = value;
+            if (e.v == &t.k2_sort || e.v == &t.k1_lattice) *e.v = value;
             else *e.v = value > 0 ? value : 0;
             return CPET_OK;
         }
@@ -192,6 +208,25 @@ int cpet_last_counters(cpet_ctx* c, int64_t out[3]) {
     CPET_REQUIRE(out != nullptr, CPET_ERR_INVALID, "out is NULL");
     if (int rc = resolve_topo_counters(c)) return rc;
     out[0] = c->last_counters[0]; out[1] = c->last_counters[1]; out[2] = c->last_counters[2];
+    return CPET_OK;
+}
+
+int cpet_kernel_times(cpet_ctx* c, double* ms, int max_n, int* n_out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(ms != nullptr && n_out != nullptr && max_n >= 0, CPET_ERR_INVALID, "bad arguments");
+    int n = c->timer_count;
+    if (n > cpet_ctx::kTimerRing) n = cpet_ctx::kTimerRing;
+    if (n > max_n) n = max_n;
+    const int first = c->timer_count - n;
+    for (int j = 0; j < n; ++j) {
+        const int i = (first + j) % cpet_ctx::kTimerRing;
+        CPET_CUDA_TRY(cudaEventSynchronize(c->ev1[i]));
+        float t = 0.f;
+        CPET_CUDA_TRY(cudaEventElapsedTime(&t, c->ev0[i], c->ev1[i]));
+        ms[j] = t;
+    }
+    *n_out = n;
+    c->timer_count = 0;
     return CPET_OK;
 }
 
@@ -246,7 +281,22 @@ int cpet_field_grid(cpet_ctx* c, int n_points, const float* x0, unsigned flags, 
     if (int rc = c->in0.reserve(sizeof(float) * 3 * n)) return rc;
     if (int rc = c->out0.reserve(sizeof(float) * out_floats)) return rc;
     CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, x0, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
-    if (int rc = cpet_field_grid_dev(c, n_points, c->in0.as<float>(), flags, c->out0.as<float>())) return rc;
+    // The reference only ever hands over mesh.reshape(-1,3) (UC:442): recognise box meshes here and
+    // give them the lattice kernel (bit-identical results, a quarter fewer FP32 instructions).
+    int is_lat = 0, nx = 0, ny = 0, nz = 0;
+    const float* d_axes = nullptr;
+    const bool try_lattice = c->tune.k1_lattice > 0 || (c->tune.k1_lattice < 0 && c->tune.k1_lanes == 0);
+    if (try_lattice) {
+        if (int rc = detect_lattice(c, n_points, c->in0.as<float>(), &is_lat, &nx, &ny, &nz, &d_axes)) return rc;
+    }
+    if (is_lat) {
+        CPET_REQUIRE((flags & ~(CPET_FIELD_SOFTEN | CPET_OUT_CONCAT)) == 0, CPET_ERR_INVALID, "unknown flag bits 0x%x", flags);
+        if (int rc = launch_field_lattice(c, field_mode_of(flags), nx, ny, nz, d_axes, d_axes + nx, d_axes + nx + ny,
+                                          (flags & CPET_OUT_CONCAT) ? 1 : 0, c->out0.p))
+            return rc;
+    } else {
+        if (int rc = cpet_field_grid_dev(c, n_points, c->in0.as<float>(), flags, c->out0.as<float>())) return rc;
+    }
     CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, sizeof(float) * out_floats, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return CPET_OK;
@@ -274,6 +324,67 @@ int cpet_esp_grid(cpet_ctx* c, int n_points, const float* x0, unsigned flags, vo
     CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return CPET_OK;
+}
+
+// ---------------------------------------------------------------- K1 on lattices -------------
+static int lattice_out_kind(int is_esp, unsigned flags) {
+    if (is_esp) return (flags & CPET_OUT_CONCAT) ? 3 : 2;
+    return (flags & CPET_OUT_CONCAT) ? 1 : 0;
+}
+static size_t lattice_out_bytes(int is_esp, unsigned flags, size_t n) {
+    if (is_esp) return (flags & CPET_OUT_CONCAT) ? 8 * n : 4 * n;
+    return sizeof(float) * ((flags & CPET_OUT_CONCAT) ? 6 * n : 3 * n);
+}
+
+static int lattice_dev(cpet_ctx* c, int is_esp, int nx, int ny, int nz, const float* d_xs, const float* d_ys,
+                       const float* d_zs, unsigned flags, void* d_out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(nx >= 0 && ny >= 0 && nz >= 0, CPET_ERR_INVALID, "negative lattice size");
+    const unsigned allowed = is_esp ? CPET_OUT_CONCAT : (CPET_FIELD_SOFTEN | CPET_OUT_CONCAT);
+    CPET_REQUIRE((flags & ~allowed) == 0, CPET_ERR_INVALID, "unknown flag bits 0x%x", flags);
+    if ((long long)nx * ny * nz == 0) return CPET_OK;
+    CPET_REQUIRE(d_xs && d_ys && d_zs && d_out, CPET_ERR_INVALID, "NULL axis/output arrays");
+    const int mode = is_esp ? MODE_ESP : field_mode_of(flags);
+    return launch_field_lattice(c, mode, nx, ny, nz, d_xs, d_ys, d_zs, lattice_out_kind(is_esp, flags), d_out);
+}
+
+static int lattice_host(cpet_ctx* c, int is_esp, int nx, int ny, int nz, const float* xs, const float* ys,
+                        const float* zs, unsigned flags, void* out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(nx >= 0 && ny >= 0 && nz >= 0, CPET_ERR_INVALID, "negative lattice size");
+    const size_t n = (size_t)nx * ny * nz;
+    if (n == 0) return CPET_OK;
+    CPET_REQUIRE(xs && ys && zs && out, CPET_ERR_INVALID, "NULL axis/output arrays");
+    const size_t ob = lattice_out_bytes(is_esp, flags, n);
+    if (int rc = c->in0.reserve(sizeof(float) * ((size_t)nx + ny + nz))) return rc;
+    if (int rc = c->out0.reserve(ob)) return rc;
+    float* d_xs = c->in0.as<float>();
+    float* d_ys = d_xs + nx;
+    float* d_zs = d_ys + ny;
+    CPET_CUDA_TRY(cudaMemcpyAsync(d_xs, xs, sizeof(float) * nx, cudaMemcpyHostToDevice, c->stream));
+    CPET_CUDA_TRY(cudaMemcpyAsync(d_ys, ys, sizeof(float) * ny, cudaMemcpyHostToDevice, c->stream));
+    CPET_CUDA_TRY(cudaMemcpyAsync(d_zs, zs, sizeof(float) * nz, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = lattice_dev(c, is_esp, nx, ny, nz, d_xs, d_ys, d_zs, flags, c->out0.p)) return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, ob, cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPET_OK;
+}
+
+int cpet_field_lattice(cpet_ctx* c, int nx, int ny, int nz, const float* xs, const float* ys, const float* zs,
+                       unsigned flags, float* out) {
+    return lattice_host(c, 0, nx, ny, nz, xs, ys, zs, flags, out);
+}
+int cpet_field_lattice_dev(cpet_ctx* c, int nx, int ny, int nz, const float* d_xs, const float* d_ys,
+                           const float* d_zs, unsigned flags, float* d_out) {
+    return lattice_dev(c, 0, nx, ny, nz, d_xs, d_ys, d_zs, flags, d_out);
+}
+int cpet_esp_lattice(cpet_ctx* c, int nx, int ny, int nz, const float* xs, const float* ys, const float* zs,
+                     unsigned flags, void* out) {
+    return lattice_host(c, 1, nx, ny, nz, xs, ys, zs, flags, out);
+}
+int cpet_esp_lattice_dev(cpet_ctx* c, int nx, int ny, int nz, const float* d_xs, const float* d_ys,
+                         const float* d_zs, unsigned flags, void* d_out) {
+    return lattice_dev(c, 1, nx, ny, nz, d_xs, d_ys, d_zs, flags, d_out);
 }
 
 int cpet_propagate_dev(cpet_ctx* c, int n_points, const float* d_x0, float step_size, float* d_out) {
@@ -390,6 +501,45 @@ int cpet_hist2d(cpet_ctx* c, int n_frames, int64_t n_per_frame, const double* va
 int cpet_hist2d_f32(cpet_ctx* c, int n_frames, int64_t n_per_frame, const float* values, int nd,
                     const double* d_edges, int nc, const double* c_edges, int64_t* counts) {
     return hist2d_host(c, n_frames, n_per_frame, values, false, nd, d_edges, nc, c_edges, counts);
+}
+
+int cpet_topo_hist(cpet_ctx* c, int n_lines, const float* seeds, const int32_t* n_iter, float step_size,
+                   const float dims[3], unsigned flags, float* out_rows, int32_t* steps, int nd,
+                   const double* d_edges, int nc, const double* c_edges, int64_t* counts) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_lines >= 0, CPET_ERR_INVALID, "n_lines < 0");
+    CPET_REQUIRE(n_lines == 0 || (seeds && n_iter), CPET_ERR_INVALID, "NULL seed/n_iter arrays");
+    CPET_REQUIRE(counts != nullptr, CPET_ERR_INVALID, "counts is NULL");
+    const double *dd, *dc;
+    if (int rc = upload_edges(c, nd, d_edges, nc, c_edges, &dd, &dc)) return rc;
+    const size_t n = (size_t)(n_lines > 0 ? n_lines : 1);
+    const size_t cbytes = sizeof(int64_t) * (size_t)nd * nc;
+    if (int rc = c->in0.reserve(sizeof(float) * 3 * n)) return rc;
+    if (int rc = c->in1.reserve(sizeof(int32_t) * n)) return rc;
+    if (int rc = c->out0.reserve(sizeof(float) * 2 * n)) return rc;
+    if (int rc = c->out1.reserve(sizeof(int32_t) * n)) return rc;
+    if (int rc = c->work0.reserve(cbytes)) return rc;
+    if (n_lines > 0) {
+        CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, seeds, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+        CPET_CUDA_TRY(cudaMemcpyAsync(c->in1.p, n_iter, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        if (int rc = cpet_topo_batch_dev(c, n_lines, c->in0.as<float>(), c->in1.as<int32_t>(), step_size, dims,
+                                         flags, c->out0.as<float>(), steps ? c->out1.as<int32_t>() : nullptr))
+            return rc;
+    }
+    const int64_t saved[3] = {c->last_counters[0], c->last_counters[1], c->last_counters[2]};
+    // the (L,2) rows never leave the device between the integrator and the binning kernel
+    if (int rc = launch_hist2d(c, 1, n_lines, c->out0.p, false, nd, dd, nc, dc, c->work0.as<unsigned long long>()))
+        return rc;
+    c->last_counters[0] = saved[0] + c->last_counters[0];
+    c->last_counters[1] = saved[1];
+    c->last_counters[2] = saved[2];
+    if (n_lines > 0 && out_rows)
+        CPET_CUDA_TRY(cudaMemcpyAsync(out_rows, c->out0.p, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (n_lines > 0 && steps)
+        CPET_CUDA_TRY(cudaMemcpyAsync(steps, c->out1.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaMemcpyAsync(counts, c->work0.p, cbytes, cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPET_OK;
 }
 
 int cpet_chi2_matrix(cpet_ctx* c, int n_hists, int64_t n_bins, const double* H, double* out) {

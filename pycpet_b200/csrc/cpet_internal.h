@@ -43,6 +43,7 @@ struct DevBuf {
 struct Tuning {
     int k1_threads = 0, k1_points = 0, k1_lanes = 0, k1_tile_pairs = 0, k1_stages = 0;
     int k1_splits = 0;
+    int k1_lattice = -1;   // -1 auto (detect z-fastest tensor-product meshes in the host entry point), 0 off, 1 on
     int k2_points = 0, k2_threads = 0, k2_lanes = 0, k2_tile_pairs = 0, k2_stages = 0, k2_ctas_per_sm = 0;
     int k2_sort = -1;   // -1 heuristic (on), 0 off, 1 on
     int timing = 0;
@@ -66,7 +67,12 @@ struct cpet_ctx {
     cpet::Tuning tune;
     int64_t last_counters[3] = {0, 0, 0};
     double last_kernel_ms = 0.0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_path = 0;               // diagnostic: 1 = the lattice kernel served the last K1 call
+    // ring of event pairs: one pair per timed kernel launch (timing=1), read back without forcing a
+    // synchronisation inside the timed region (cpet_kernel_times)
+    static constexpr int kTimerRing = 256;
+    cudaEvent_t ev0[kTimerRing] = {}, ev1[kTimerRing] = {};
+    int timer_count = 0;      // launches recorded since the last cpet_kernel_times()
 };
 
 namespace cpet {
@@ -78,6 +84,13 @@ int launch_pack_charges(cpet_ctx* c, int n_charges, const float* d_x, const floa
 //                4 = (N,3) f32 p + step*E/|E|
 int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, int out_kind,
                       void* d_out, float step = 0.0f);
+
+// K1 on a tensor-product lattice xs x ys x zs (z fastest); same out_kind codes
+int launch_field_lattice(cpet_ctx* c, int mode, int nx, int ny, int nz, const float* d_xs,
+                         const float* d_ys, const float* d_zs, int out_kind, void* d_out);
+
+int detect_lattice(cpet_ctx* c, int n_points, const float* d_x0, int* is_lattice, int* nx, int* ny,
+                   int* nz, const float** d_axes);
 
 // K2
 int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d_n_iter,

@@ -218,6 +218,221 @@ __global__ void k1_finalize_kernel(const double* __restrict__ partial, int split
                  s0, s1, s2);
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1-lattice: the same kernel for tensor-product grids (see common.cuh: eval_pair_lattice).
+// Work item = PZ consecutive z-nodes of one (x,y) column; point id = (ix*ny + iy)*nz + iz.
+// ---------------------------------------------------------------------------------------------
+struct K1LatParams {
+    const ChargePair* charges;
+    int n_pairs;
+    int pairs_per_split;
+    int tile_pairs;
+    int stages;
+    const float* xs;
+    const float* ys;
+    const float* zs;
+    int nx, ny, nz, nzb;    // nzb = ceil(nz / PZ) z-blocks per column
+    int n_items;            // nx * ny * nzb
+    int n_points;
+    int out_kind;
+    float step;
+    void* out;
+    double* partial;
+};
+
+template <int MODE, int PZ>
+__global__ void __launch_bounds__(256) k1_lattice_kernel(const K1LatParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    ChargePair* ring = reinterpret_cast<ChargePair*>(smem_raw + 128);
+
+    const int tid = threadIdx.x;
+    const int S = prm.stages;
+    const int TP = prm.tile_pairs;
+    const int pbeg = blockIdx.y * prm.pairs_per_split;
+    const int pend = min(prm.n_pairs, pbeg + prm.pairs_per_split);
+    const int npairs = max(0, pend - pbeg);
+    const int ntiles = (npairs + TP - 1) / TP;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const int stage = t % S;
+        const int n_t = min(TP, npairs - t * TP);
+        const uint32_t bytes = (uint32_t)n_t * (uint32_t)sizeof(ChargePair);
+        mbar_expect_tx(&full[stage], bytes);
+        tma_load_1d(ring + (size_t)stage * TP, prm.charges + pbeg + (size_t)t * TP, bytes,
+                    &full[stage]);
+    };
+    if (tid == 0) {
+        const int pre = min(S, ntiles);
+        for (int t = 0; t < pre; ++t) issue(t);
+    }
+
+    // this thread's column and z-block
+    const int item = min(blockIdx.x * blockDim.x + tid, prm.n_items - 1);
+    const bool live = (blockIdx.x * blockDim.x + tid) < prm.n_items;
+    const int col = item / prm.nzb;
+    const int zb = item - col * prm.nzb;
+    const int ix = col / prm.ny;
+    const int iy = col - ix * prm.ny;
+    const float x = prm.xs[ix], y = prm.ys[iy];
+    float z[PZ];
+    LatticeRegs<PZ> r;
+    double acc[PZ][3];
+    r.px = pk2(x, x);
+    r.py = pk2(y, y);
+#pragma unroll
+    for (int p = 0; p < PZ; ++p) {
+        z[p] = prm.zs[min(zb * PZ + p, prm.nz - 1)];
+        r.pz[p] = pk2(z[p], z[p]);
+        r.ax[p] = r.ay[p] = r.az[p] = 0ull;
+        acc[p][0] = acc[p][1] = acc[p][2] = 0.0;
+    }
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int stage = t % S;
+        mbar_wait(&full[stage], (uint32_t)((t / S) & 1));
+        const int n_t = min(TP, npairs - t * TP);
+        eval_tile_lattice_chunked<MODE, PZ, 2, 64>(ring + (size_t)stage * TP, n_t, r, acc);
+        if (t + S < ntiles) {
+            __syncthreads();
+            if (tid == 0) issue(t + S);
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int p = 0; p < PZ; ++p) {
+        const int iz = zb * PZ + p;
+        if (iz >= prm.nz) continue;
+        const int pt = col * prm.nz + iz;
+        if (gridDim.y == 1) {
+            store_result(prm.out_kind, prm.step, prm.out, pt, x, y, z[p], acc[p][0], acc[p][1], acc[p][2]);
+        } else {
+            double* o = prm.partial + ((size_t)blockIdx.y * prm.n_points + pt) * 3;
+            o[0] = acc[p][0]; o[1] = acc[p][1]; o[2] = acc[p][2];
+        }
+    }
+}
+
+// finalize for the lattice path: coordinates come from the axis arrays
+__global__ void k1_lattice_finalize_kernel(const double* __restrict__ partial, int splits, int n_points,
+                                           const float* __restrict__ xs, const float* __restrict__ ys,
+                                           const float* __restrict__ zs, int ny, int nz, int out_kind,
+                                           float step, void* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_points) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int s = 0; s < splits; ++s) {
+        const double* p = partial + ((size_t)s * n_points + i) * 3;
+        s0 += p[0]; s1 += p[1]; s2 += p[2];
+    }
+    const int iz = i % nz;
+    const int col = i / nz;
+    store_result(out_kind, step, out, i, xs[col / ny], ys[col % ny], zs[iz], s0, s1, s2);
+}
+
+template <int MODE, int PZ>
+static int launch_k1_lat_inst(cpet_ctx* c, const K1LatParams& prm, dim3 grid, int threads, size_t smem) {
+    auto kern = k1_lattice_kernel<MODE, PZ>;
+    CPET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, c->stream>>>(prm);
+    CPET_CUDA_TRY(cudaGetLastError());
+    return CPET_OK;
+}
+
+int launch_field_lattice(cpet_ctx* c, int mode, int nx, int ny, int nz, const float* d_xs,
+                         const float* d_ys, const float* d_zs, int out_kind, void* d_out) {
+    const long long n_points_ll = (long long)nx * ny * nz;
+    c->last_counters[0] = 0;
+    c->last_counters[1] = n_points_ll * (long long)c->n_charges;
+    c->last_counters[2] = n_points_ll;
+    if (n_points_ll == 0) return CPET_OK;
+    CPET_REQUIRE(n_points_ll <= 0x7fffffffLL, CPET_ERR_INVALID, "lattice too large (%lld points)", n_points_ll);
+    const int n_points = (int)n_points_ll;
+    const Tuning& tu = c->tune;
+    const int sms = c->sm_count;
+    const int threads = 256;
+    int PZ = tu.k1_points > 0 ? tu.k1_points : 4;
+    if (PZ != 2 && PZ != 4 && PZ != 5) PZ = 4;
+    const int nzb = (nz + PZ - 1) / PZ;
+    const long long n_items_ll = (long long)nx * ny * nzb;
+    const int n_items = (int)n_items_ll;
+    const int gx = (n_items + threads - 1) / threads;
+
+    int splits = tu.k1_splits;
+    if (splits <= 0) {
+        splits = 1;
+        const double slots = 2.0 * sms;
+        const int smax = c->n_pairs / 1024 > 16 ? 16 : c->n_pairs / 1024;
+        double best = 1e30;
+        for (int s = 1; s <= (smax < 1 ? 1 : smax); ++s) {
+            const double w = (double)gx * s / slots;
+            const double ineff = ceil(w) / w;
+            if (ineff < best - 0.004) { best = ineff; splits = s; }
+            if (ineff <= 1.02) break;
+        }
+    }
+    while (splits > 1 && (size_t)splits * (size_t)n_points * 24u > ((size_t)1 << 30)) --splits;
+    int pps = (c->n_pairs + splits - 1) / splits;
+    pps = ((pps + 7) / 8) * 8;
+    if (pps < 8) pps = 8;
+    splits = c->n_pairs > 0 ? (c->n_pairs + pps - 1) / pps : 1;
+    int tile_pairs = tu.k1_tile_pairs > 0 ? tu.k1_tile_pairs : 1024;
+    if (tile_pairs > pps) tile_pairs = pps;
+    tile_pairs = ((tile_pairs + 7) / 8) * 8;
+    int stages = tu.k1_stages > 0 ? tu.k1_stages : 3;
+    if (stages > 8) stages = 8;
+    const int ntiles = (pps + tile_pairs - 1) / tile_pairs;
+    if (stages > ntiles) stages = ntiles;
+    if (stages < 1) stages = 1;
+    const size_t smem = 128 + (size_t)stages * tile_pairs * sizeof(ChargePair);
+
+    K1LatParams prm;
+    prm.charges = c->charges.as<ChargePair>();
+    prm.n_pairs = c->n_pairs;
+    prm.pairs_per_split = pps;
+    prm.tile_pairs = tile_pairs;
+    prm.stages = stages;
+    prm.xs = d_xs; prm.ys = d_ys; prm.zs = d_zs;
+    prm.nx = nx; prm.ny = ny; prm.nz = nz; prm.nzb = nzb;
+    prm.n_items = n_items;
+    prm.n_points = n_points;
+    prm.out_kind = out_kind;
+    prm.step = 0.f;
+    prm.out = d_out;
+    prm.partial = nullptr;
+    if (splits > 1) {
+        if (int rc = c->work0.reserve(sizeof(double) * 3 * (size_t)splits * (size_t)n_points)) return rc;
+        prm.partial = c->work0.as<double>();
+    }
+    KernelTimer timer(c);
+    dim3 grid((unsigned)gx, (unsigned)splits, 1);
+    int rc;
+#define CPET_LAT_CASE(M)                                                                    \
+    (PZ == 2 ? launch_k1_lat_inst<M, 2>(c, prm, grid, threads, smem)                         \
+             : (PZ == 5 ? launch_k1_lat_inst<M, 5>(c, prm, grid, threads, smem)              \
+                        : launch_k1_lat_inst<M, 4>(c, prm, grid, threads, smem)))
+    if (mode == MODE_FIELD_SOFT) rc = CPET_LAT_CASE(MODE_FIELD_SOFT);
+    else if (mode == MODE_FIELD_RAW) rc = CPET_LAT_CASE(MODE_FIELD_RAW);
+    else rc = CPET_LAT_CASE(MODE_ESP);
+#undef CPET_LAT_CASE
+    if (rc) return rc;
+    c->last_counters[0] = 1;
+    c->last_path = 1;
+    if (splits > 1) {
+        k1_lattice_finalize_kernel<<<(n_points + 255) / 256, 256, 0, c->stream>>>(
+            prm.partial, splits, n_points, d_xs, d_ys, d_zs, ny, nz, out_kind, 0.f, d_out);
+        CPET_CUDA_TRY(cudaGetLastError());
+        c->last_counters[0] = 2;
+    }
+    return CPET_OK;
+}
+
 template <int MODE, int P, int G>
 static int launch_k1_inst(cpet_ctx* c, const K1Params& prm, dim3 grid, int threads, size_t smem) {
     auto kern = k1_grid_kernel<MODE, P, G>;
@@ -237,6 +452,82 @@ static int launch_k1_mode(cpet_ctx* c, const K1Params& prm, int P, int G, dim3 g
     }
     if (G == 8) return launch_k1_inst<MODE, 1, 8>(c, prm, grid, threads, smem);
     return launch_k1_inst<MODE, 1, 32>(c, prm, grid, threads, smem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lattice detection on a flat (N,3) point list, so that the reference-shaped entry point
+// (compute_looped_field / cpet_field_grid, which only ever sees mesh.reshape(-1,3)) can take the
+// lattice kernel by itself.  Exact: every point is compared against the inferred axes.
+//   info[0] = nz (first index where x or y changes), info[1] = ny*nz (first index where x changes),
+//   info[2] = 1 if every point equals (x[(i/nynz)*nynz], y[((i/nz)%ny)*nz], z[i%nz]).
+// ---------------------------------------------------------------------------------------------
+__global__ void lattice_probe_kernel(const float* __restrict__ p, int n, unsigned* __restrict__ info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= 0 || i >= n) return;
+    const bool dx = p[3 * (size_t)i] != p[0];
+    const bool dy = p[3 * (size_t)i + 1] != p[1];
+    // only the first change matters: a point whose predecessor already differs cannot be the minimum
+    if (dx || dy) {
+        const bool pdx = p[3 * (size_t)(i - 1)] != p[0];
+        const bool pdy = p[3 * (size_t)(i - 1) + 1] != p[1];
+        if (!(pdx || pdy)) atomicMin(&info[0], (unsigned)i);
+        if (dx && !pdx) atomicMin(&info[1], (unsigned)i);
+    }
+}
+
+__global__ void lattice_verify_kernel(const float* __restrict__ p, int n, unsigned* __restrict__ info) {
+    const unsigned nz = info[0], nynz = info[1] == 0xffffffffu ? (unsigned)n : info[1];
+    if (nz == 0xffffffffu || nz == 0 || nynz % nz != 0 || (unsigned)n % nynz != 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) info[2] = 0;
+        return;
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned ix = (unsigned)i / nynz, rem = (unsigned)i % nynz;
+    const unsigned iy = rem / nz, iz = rem % nz;
+    const bool ok = p[3 * (size_t)i] == p[3 * (size_t)(ix * nynz)] &&
+                    p[3 * (size_t)i + 1] == p[3 * (size_t)(iy * nz) + 1] &&
+                    p[3 * (size_t)i + 2] == p[3 * (size_t)iz + 2];
+    if (!ok) info[2] = 0;
+}
+
+__global__ void lattice_axes_kernel(const float* __restrict__ p, int nx, int ny, int nz,
+                                    float* __restrict__ axes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nx) axes[i] = p[3 * (size_t)i * ny * nz];
+    else if (i < nx + ny) axes[i] = p[3 * (size_t)(i - nx) * nz + 1];
+    else if (i < nx + ny + nz) axes[i] = p[3 * (size_t)(i - nx - ny) + 2];
+}
+
+// Returns 1 in *is_lattice (and the sizes + a device array xs|ys|zs in c->work2) when the point list
+// is a z-fastest tensor-product mesh with nz >= 4.  Synchronises the stream once (12-byte readback).
+int detect_lattice(cpet_ctx* c, int n_points, const float* d_x0, int* is_lattice, int* nx, int* ny,
+                   int* nz, const float** d_axes) {
+    *is_lattice = 0;
+    if (n_points < 4096) return CPET_OK;
+    if (int rc = c->counters.reserve(64 + sizeof(unsigned) * 3 * 2048)) return rc;
+    unsigned* info = reinterpret_cast<unsigned*>(c->counters.as<unsigned char>() + 16);
+    const unsigned init[3] = {0xffffffffu, 0xffffffffu, 1u};
+    CPET_CUDA_TRY(cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    const int blocks = (n_points + 255) / 256;
+    lattice_probe_kernel<<<blocks, 256, 0, c->stream>>>(d_x0, n_points, info);
+    lattice_verify_kernel<<<blocks, 256, 0, c->stream>>>(d_x0, n_points, info);
+    CPET_CUDA_TRY(cudaGetLastError());
+    unsigned h[3] = {0, 0, 0};
+    CPET_CUDA_TRY(cudaMemcpyAsync(h, info, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (h[2] != 1u || h[0] == 0xffffffffu || h[0] < 4) return CPET_OK;
+    const unsigned nynz = h[1] == 0xffffffffu ? (unsigned)n_points : h[1];
+    *nz = (int)h[0];
+    *ny = (int)(nynz / h[0]);
+    *nx = (int)((unsigned)n_points / nynz);
+    const int na = *nx + *ny + *nz;
+    if (int rc = c->work2.reserve(sizeof(float) * (size_t)na)) return rc;
+    lattice_axes_kernel<<<(na + 255) / 256, 256, 0, c->stream>>>(d_x0, *nx, *ny, *nz, c->work2.as<float>());
+    CPET_CUDA_TRY(cudaGetLastError());
+    *d_axes = c->work2.as<float>();
+    *is_lattice = 1;
+    return CPET_OK;
 }
 
 int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, int out_kind,
@@ -279,8 +570,26 @@ int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, in
     int splits = tu.k1_splits;
     if (splits <= 0) {
         splits = 1;
-        if (gx < 2 * sms) splits = (2 * sms + gx - 1) / gx;
+        if (gx < 2 * sms) {
+            splits = (2 * sms + gx - 1) / gx;
+        } else {
+            // Wave quantisation: with ~2 resident CTAs/SM a grid of gx equal CTAs takes
+            // ceil(gx / (2*sms)) rounds.  Splitting the charge range makes more, shorter CTAs so the
+            // last round is nearly full (measured: 1007 CTAs 2.46e12 -> 16 splits 2.54e12
+            // pair-evals/s, profiles/round1_tail_test.txt).  Keep >= 1024 pairs per split.
+            const double slots = 2.0 * sms;
+            const int smax = c->n_pairs / 1024 > 16 ? 16 : c->n_pairs / 1024;
+            double best = 1e30;
+            for (int s = 1; s <= (smax < 1 ? 1 : smax); ++s) {
+                const double w = (double)gx * s / slots;
+                const double ineff = ceil(w) / w;
+                if (ineff < best - 0.004) { best = ineff; splits = s; }
+                if (ineff <= 1.02) break;
+            }
+        }
     }
+    // FP64 partials cost 24 B per point per split: keep that scratch under 1 GiB
+    while (splits > 1 && (size_t)splits * (size_t)n_points * 24u > ((size_t)1 << 30)) --splits;
     const int min_pairs_per_split = 64;
     int max_splits = c->n_pairs / min_pairs_per_split;
     if (max_splits < 1) max_splits = 1;
@@ -330,6 +639,7 @@ int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, in
     else rc = launch_k1_mode<MODE_ESP>(c, prm, P, G, grid, threads, smem);
     if (rc) return rc;
     c->last_counters[0] = 1;
+    c->last_path = 0;
     if (splits > 1) {
         k1_finalize_kernel<<<(n_points + 255) / 256, 256, 0, c->stream>>>(
             prm.partial, splits, n_points, d_x0, out_kind, step, d_out);

@@ -25,6 +25,9 @@
 namespace cpet {
 
 #define K2_KEYMAX 2048
+#ifndef CPET_K2_UNROLL
+#define CPET_K2_UNROLL 8
+#endif
 
 struct K2Params {
     const ChargePair* charges;
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(512, 1) k2_topo_kernel(const K2Params prm) {
         if (prm.resident) {
             for (int t = 0; t < NT; ++t) {
                 const int n_t = min(TP, prm.n_pairs - t * TP);
-                eval_tile_chunked<MODE_FIELD_RAW, P, (P >= 2 ? 2 : 4), 64>(ring + (size_t)t * TP, lane_g,
+                eval_tile_chunked<MODE_FIELD_RAW, P, (P >= 2 ? 2 : CPET_K2_UNROLL), 64>(ring + (size_t)t * TP, lane_g,
                                                                            n_t, G, r, acc);
             }
         } else {
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(512, 1) k2_topo_kernel(const K2Params prm) {
                 mbar_wait(&full[stage], (uint32_t)((it / S) & 1));
                 if (warp_on) {
                     const int n_t = min(TP, prm.n_pairs - t * TP);
-                    eval_tile_chunked<MODE_FIELD_RAW, P, (P >= 2 ? 2 : 4), 64>(
+                    eval_tile_chunked<MODE_FIELD_RAW, P, (P >= 2 ? 2 : CPET_K2_UNROLL), 64>(
                         ring + (size_t)stage * TP, lane_g, n_t, G, r, acc);
                 }
                 __syncthreads();                      // stage fully consumed by the CTA
@@ -324,18 +327,27 @@ __global__ void __launch_bounds__(256) k2_count_kernel(const int32_t* __restrict
         if (cnt[i]) atomicAdd(&hist[i], cnt[i]);
 }
 
-// offsets[key] = number of lines with a LARGER key (descending order); one block.
+// offsets[key] = number of lines with a LARGER key (descending order); one block of 1024 threads,
+// two keys per thread, Hillis-Steele inclusive scan over the per-thread sums.
 __global__ void __launch_bounds__(1024) k2_scan_kernel(const unsigned* __restrict__ hist,
                                                        unsigned* __restrict__ offsets) {
-    __shared__ unsigned s[K2_KEYMAX];
-    for (int i = threadIdx.x; i < K2_KEYMAX; i += blockDim.x) s[i] = hist[K2_KEYMAX - 1 - i];
+    static_assert(K2_KEYMAX == 2048, "scan assumes 2 keys per thread");
+    __shared__ unsigned s[1024];
+    const int t = threadIdx.x;
+    // reversed order: position i holds key K2_KEYMAX-1-i
+    const unsigned a = hist[K2_KEYMAX - 1 - 2 * t];
+    const unsigned b = hist[K2_KEYMAX - 2 - 2 * t];
+    s[t] = a + b;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned run = 0;
-        for (int i = 0; i < K2_KEYMAX; ++i) { const unsigned c = s[i]; s[i] = run; run += c; }
+    for (int d = 1; d < 1024; d <<= 1) {
+        const unsigned v = (t >= d) ? s[t - d] : 0u;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < K2_KEYMAX; i += blockDim.x) offsets[K2_KEYMAX - 1 - i] = s[i];
+    const unsigned excl = s[t] - (a + b);
+    offsets[K2_KEYMAX - 1 - 2 * t] = excl;
+    offsets[K2_KEYMAX - 2 - 2 * t] = excl + a;
 }
 
 __global__ void __launch_bounds__(256) k2_scatter_kernel(const int32_t* __restrict__ n_iter, int n,

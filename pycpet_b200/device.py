@@ -71,6 +71,13 @@ class Engine:
         check(self.lib.cpet_last_kernel_ms(self.ctx, ctypes.byref(ms)))
         return float(ms.value)
 
+    def kernel_times(self):
+        """Durations (ms) of the dominant-kernel launches since the last call (timing=1)."""
+        buf = (ctypes.c_double * 256)()
+        n = ctypes.c_int(0)
+        check(self.lib.cpet_kernel_times(self.ctx, buf, 256, ctypes.byref(n)))
+        return [float(buf[i]) for i in range(n.value)]
+
     def fp32_peak_tflops(self, packed=True, iters=4096) -> float:
         t = ctypes.c_double(0.0)
         check(self.lib.cpet_fp32_peak_probe(self.ctx, int(bool(packed)), int(iters), ctypes.byref(t)))
@@ -104,6 +111,30 @@ class Engine:
                    else torch.empty(n, dtype=torch.float32, device=self.device))
         check(self.lib.cpet_esp_grid_dev(self.ctx, n, _p(x0), _lib.CPET_OUT_CONCAT if concat_half else 0,
                                          _p(out)))
+        return out
+
+    def field_lattice(self, xs, ys, zs, soften=True, concat=False, out=None):
+        torch = self.torch
+        xs, ys, zs = self._f32(xs).reshape(-1), self._f32(ys).reshape(-1), self._f32(zs).reshape(-1)
+        n = xs.shape[0] * ys.shape[0] * zs.shape[0]
+        if out is None:
+            out = torch.empty((n, 6 if concat else 3), dtype=torch.float32, device=self.device)
+        flags = (_lib.CPET_FIELD_SOFTEN if soften else 0) | (_lib.CPET_OUT_CONCAT if concat else 0)
+        check(self.lib.cpet_field_lattice_dev(self.ctx, xs.shape[0], ys.shape[0], zs.shape[0], _p(xs), _p(ys),
+                                              _p(zs), flags, _p(out)))
+        self._keep4 = (xs, ys, zs)
+        return out
+
+    def esp_lattice(self, xs, ys, zs, concat_half=False, out=None):
+        torch = self.torch
+        xs, ys, zs = self._f32(xs).reshape(-1), self._f32(ys).reshape(-1), self._f32(zs).reshape(-1)
+        n = xs.shape[0] * ys.shape[0] * zs.shape[0]
+        if out is None:
+            out = (torch.empty((n, 4), dtype=torch.float16, device=self.device) if concat_half
+                   else torch.empty(n, dtype=torch.float32, device=self.device))
+        check(self.lib.cpet_esp_lattice_dev(self.ctx, xs.shape[0], ys.shape[0], zs.shape[0], _p(xs), _p(ys),
+                                            _p(zs), _lib.CPET_OUT_CONCAT if concat_half else 0, _p(out)))
+        self._keep4 = (xs, ys, zs)
         return out
 
     def propagate(self, x0, step_size, out=None):

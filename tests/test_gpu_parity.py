@@ -44,6 +44,7 @@ def frame2a(golden):
 
 def reset_tuning(m):
     m.set_tuning(k1_threads=0, k1_points=0, k1_lanes=0, k1_tile_pairs=0, k1_stages=0, k1_splits=0,
+                 k1_lattice=-1,
                  k2_points=0, k2_threads=0, k2_lanes=0, k2_tile_pairs=0, k2_stages=0, k2_sort=-1)
 
 
@@ -185,6 +186,93 @@ def test_field_full_size_properties(M):
     assert relmax(e[idx], f64.field_grid(pts[idx], x, Q, True)) < FIELD_TOL
     phi = M.esp_grid(pts)
     assert relmax(phi[idx], f64.esp_grid(pts[idx], x, Q)) < FIELD_TOL
+
+
+@pytest.mark.parametrize("shape", [(11, 11, 11), (5, 7, 23), (3, 2, 101), (6, 5, 4), (2, 3, 1)])
+def test_field_lattice_matches_general_kernel(M, frame2a, shape):
+    """The lattice kernel (dx, dy shared along z) against the general kernel on the expanded mesh:
+    bit-identical with the charge range unsplit, and within 1e-5 of the oracle."""
+    x, Q = frame2a
+    nx, ny, nz = shape
+    xs = np.linspace(-0.5, 0.5, nx, dtype=np.float32)
+    ys = np.linspace(-0.4, 0.6, ny, dtype=np.float32)
+    zs = np.linspace(-0.7, 0.3, nz, dtype=np.float32)
+    mesh = np.stack(np.meshgrid(xs, ys, zs, indexing="ij"), axis=-1).astype(np.float32)
+    pts = mesh.reshape(-1, 3)
+    M.set_charges(x, Q)
+    reset_tuning(M)
+    try:
+        for pz in (2, 4, 5):
+            M.set_tuning(k1_splits=1, k1_lanes=1, k1_points=pz)
+            for soften in (True, False):
+                lat = M.field_lattice(xs, ys, zs, soften=soften, concat=True)
+                M.set_tuning(k1_points=4 if pz == 5 else pz)
+                gen = M.field_grid(pts, soften=soften, concat=True)
+                M.set_tuning(k1_points=pz)
+                np.testing.assert_array_equal(lat, gen)
+            lat_esp = M.esp_lattice(xs, ys, zs, concat_half=True)
+            np.testing.assert_array_equal(lat_esp, M.esp_grid(pts, concat_half=True))
+        reset_tuning(M)
+        # default heuristics (charge splits may differ between the two paths): oracle parity
+        lat = M.field_lattice(xs, ys, zs, soften=True)
+        assert relmax(lat, f64.field_grid(pts, x, Q, True)) < FIELD_TOL
+        assert relmax(M.esp_lattice(xs, ys, zs), f64.esp_grid(pts, x, Q)) < FIELD_TOL
+    finally:
+        reset_tuning(M)
+    # the calculator-level entry point picks the lattice path for box meshes and only for them
+    from pycpet_b200 import calculator as calc
+    assert (calc.lattice_axes(mesh) is not None)
+    bumped = mesh.copy()
+    bumped[0, 0, 0, 2] += np.float32(1e-3)
+    assert calc.lattice_axes(bumped) is None
+    out = calc.compute_field_on_grid(mesh, x, Q)
+    assert out.shape == (len(pts), 6)
+    np.testing.assert_array_equal(out[:, :3], pts)
+    assert relmax(out[:, 3:], f64.field_grid(pts, x, Q, True)) < FIELD_TOL
+    assert relmax(calc.compute_field_on_grid(bumped, x, Q)[:, 3:],
+                  f64.field_grid(bumped.reshape(-1, 3), x, Q, True)) < FIELD_TOL
+
+
+def test_field_grid_recognises_box_meshes(M, frame2a):
+    """compute_looped_field only ever receives mesh.reshape(-1,3): the library detects the
+    tensor-product structure on the device and switches kernels without changing a single bit."""
+    x, Q = frame2a
+    reset_tuning(M)
+    M.set_charges(x, Q)
+    for shape in [(17, 17, 17), (9, 31, 40), (1, 64, 64), (4096, 1, 4), (33, 33, 5)]:
+        axes = [np.linspace(-0.5, 0.5 + 0.1 * i, n, dtype=np.float32) for i, n in enumerate(shape)]
+        mesh = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).astype(np.float32)
+        pts = mesh.reshape(-1, 3)
+        M.set_tuning(k1_lattice=-1, k1_splits=1)
+        auto = M.field_grid(pts, soften=True, concat=True)
+        assert M.last_path() == "lattice", shape
+        M.set_tuning(k1_lattice=0, k1_splits=1, k1_points=4, k1_lanes=1)
+        gen = M.field_grid(pts, soften=True, concat=True)
+        assert M.last_path() == "general"
+        np.testing.assert_array_equal(auto, gen)
+        reset_tuning(M)
+        M.set_tuning(k1_lattice=-1)
+        # anything that is not exactly a z-fastest mesh keeps the general kernel
+        for bad in (pts[::-1].copy(), pts[np.random.default_rng(0).permutation(len(pts))],
+                    np.ascontiguousarray(mesh.transpose(2, 1, 0, 3)).reshape(-1, 3)):
+            if np.array_equal(bad, pts):
+                continue
+            got = M.field_grid(bad, soften=True)
+            if M.last_path() == "lattice":      # e.g. a reversed mesh is still a valid mesh
+                assert relmax(got, f64.field_grid(bad, x, Q, True)) < FIELD_TOL
+            else:
+                assert relmax(got, f64.field_grid(bad, x, Q, True)) < FIELD_TOL
+        bumped = pts.copy()
+        bumped[len(pts) // 2, 1] += np.float32(1e-4)
+        got = M.field_grid(bumped, soften=True)
+        assert M.last_path() == "general"
+        assert relmax(got, f64.field_grid(bumped, x, Q, True)) < FIELD_TOL
+    # legacy symbol goes through the same host entry point
+    axes = [np.linspace(-0.5, 0.5, 17, dtype=np.float32)] * 3
+    pts = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).astype(np.float32).reshape(-1, 3)
+    e = M.compute_looped_field(pts, x, Q)
+    assert relmax(e, f64.field_grid(pts, x, Q, True)) < FIELD_TOL
+    reset_tuning(M)
 
 
 def test_propagate(M, frame2a):
@@ -393,6 +481,29 @@ def test_make_histograms_and_chi2(M, tmp_path):
     np.testing.assert_allclose(D, Dw, rtol=1e-12, atol=1e-15)
     assert np.all(np.diag(D) == 0) and np.allclose(D, D.T, rtol=0, atol=0)
     assert abs(calc.distance_numpy(H[0], H[1]) - ohist.chi2(want[0], want[1])) < 1e-14
+
+
+def test_topo_hist_fused_call(M, frame2a):
+    """cpet_topo_hist = cpet_topo_batch + cpet_hist2d with the rows kept on the device."""
+    x, Q = frame2a
+    seeds, n_iter, dims, _ = synth.seeds(14, 0.5, 0.1)
+    de, ce = np.linspace(0, 1.8, 31), np.linspace(0, 3.0, 41)
+    M.set_charges(x, Q)
+    rows = M.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims)
+    out = np.zeros((len(seeds), 2), np.float32)
+    rows2, counts = M.topo_hist(seeds, n_iter, de, ce, step_size=0.1, dimensions=dims, out=out)
+    assert rows2 is out
+    np.testing.assert_array_equal(rows2, rows)
+    want, _, _ = np.histogram2d(rows[:, 0].astype(np.float64), rows[:, 1].astype(np.float64),
+                                bins=[30, 40], range=[(0, 1.8), (0, 3.0)])
+    np.testing.assert_array_equal(counts, want.astype(np.int64))
+    c = M.last_counters()
+    assert c["pair_evals"] > 0 and c["launches"] >= 2
+    none_rows, counts2 = M.topo_hist(seeds, n_iter, de, ce, step_size=0.1, dimensions=dims, want_rows=False)
+    assert none_rows is None
+    np.testing.assert_array_equal(counts2, counts)
+    with pytest.raises(ValueError):
+        M.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, out=np.zeros((3, 2), np.float32))
 
 
 # --------------------------------------------------------------------------- legacy symbols -----
