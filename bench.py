@@ -210,7 +210,10 @@ def run_gpu(args, rank, world, local_rank):
         elif kind == "field":
             # device arm: the mesh is described by its axes (what the host entry point derives from the
             # flat list by itself, see cpet_field_grid); the e2e arm below hands over the flat list
-            eng.field_lattice(daxis, daxis, daxis, soften=True, concat=True, out=dout)
+            if n >= 4096:
+                eng.field_lattice(daxis, daxis, daxis, soften=True, concat=True, out=dout)
+            else:            # below the library's own mesh-detection threshold: general kernel
+                eng.field_grid(dpts, soften=True, concat=True, out=dout)
             if probe:
                 c = eng.last_counters()
                 work["pairs"], work["units"], work["k_launch"] = c["pair_evals"], len(inp["points"]), c["launches"]

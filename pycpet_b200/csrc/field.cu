@@ -240,7 +240,7 @@ struct K1LatParams {
     double* partial;
 };
 
-template <int MODE, int PZ>
+template <int MODE, int PZ, int U>
 __global__ void __launch_bounds__(256) k1_lattice_kernel(const K1LatParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) k1_lattice_kernel(const K1LatParams prm) 
         const int stage = t % S;
         mbar_wait(&full[stage], (uint32_t)((t / S) & 1));
         const int n_t = min(TP, npairs - t * TP);
-        eval_tile_lattice_chunked<MODE, PZ, 2, 64>(ring + (size_t)stage * TP, n_t, r, acc);
+        eval_tile_lattice_chunked<MODE, PZ, U, 64>(ring + (size_t)stage * TP, n_t, r, acc);
         if (t + S < ntiles) {
             __syncthreads();
             if (tid == 0) issue(t + S);
@@ -336,9 +336,9 @@ __global__ void k1_lattice_finalize_kernel(const double* __restrict__ partial, i
     store_result(out_kind, step, out, i, xs[col / ny], ys[col % ny], zs[iz], s0, s1, s2);
 }
 
-template <int MODE, int PZ>
+template <int MODE, int PZ, int U>
 static int launch_k1_lat_inst(cpet_ctx* c, const K1LatParams& prm, dim3 grid, int threads, size_t smem) {
-    auto kern = k1_lattice_kernel<MODE, PZ>;
+    auto kern = k1_lattice_kernel<MODE, PZ, U>;
     CPET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, c->stream>>>(prm);
     CPET_CUDA_TRY(cudaGetLastError());
@@ -357,15 +357,25 @@ int launch_field_lattice(cpet_ctx* c, int mode, int nx, int ny, int nz, const fl
     const Tuning& tu = c->tune;
     const int sms = c->sm_count;
     const int threads = 256;
-    int PZ = tu.k1_points > 0 ? tu.k1_points : 4;
-    if (PZ != 2 && PZ != 4 && PZ != 5) PZ = 4;
+    // measured (profiles/round1_lattice_sweep.txt): 5 z-nodes/thread + unroll 4 is fastest (3.05e12
+    // pair-evals/s at 100^3 x 100k); take 4 nodes when that pads the z axis noticeably less
+    int PZ = tu.k1_points;
+    if (PZ != 2 && PZ != 4 && PZ != 5) {
+        const double pad5 = (double)((nz + 4) / 5 * 5) / nz, pad4 = (double)((nz + 3) / 4 * 4) / nz;
+        PZ = (pad5 <= pad4 * 1.02) ? 5 : 4;
+    }
     const int nzb = (nz + PZ - 1) / PZ;
     const long long n_items_ll = (long long)nx * ny * nzb;
     const int n_items = (int)n_items_ll;
     const int gx = (n_items + threads - 1) / threads;
 
     int splits = tu.k1_splits;
-    if (splits <= 0) {
+    if (splits <= 0 && gx < 2 * sms) {
+        // small mesh: fill the chip by splitting the charge range (>= 64 pairs per split)
+        splits = (2 * sms + gx - 1) / gx;
+        const int cap = c->n_pairs / 64 > 0 ? c->n_pairs / 64 : 1;
+        if (splits > cap) splits = cap;
+    } else if (splits <= 0) {
         splits = 1;
         const double slots = 2.0 * sms;
         const int smax = c->n_pairs / 1024 > 16 ? 16 : c->n_pairs / 1024;
@@ -413,14 +423,17 @@ int launch_field_lattice(cpet_ctx* c, int mode, int nx, int ny, int nz, const fl
     KernelTimer timer(c);
     dim3 grid((unsigned)gx, (unsigned)splits, 1);
     int rc;
-#define CPET_LAT_CASE(M)                                                                    \
-    (PZ == 2 ? launch_k1_lat_inst<M, 2>(c, prm, grid, threads, smem)                         \
-             : (PZ == 5 ? launch_k1_lat_inst<M, 5>(c, prm, grid, threads, smem)              \
-                        : launch_k1_lat_inst<M, 4>(c, prm, grid, threads, smem)))
+    const int U = tu.k1_unroll == 1 ? 1 : (tu.k1_unroll == 2 ? 2 : 4);
+#define CPET_LAT_PZ(M, UU)                                                                  \
+    (PZ == 2 ? launch_k1_lat_inst<M, 2, UU>(c, prm, grid, threads, smem)                     \
+             : (PZ == 5 ? launch_k1_lat_inst<M, 5, UU>(c, prm, grid, threads, smem)          \
+                        : launch_k1_lat_inst<M, 4, UU>(c, prm, grid, threads, smem)))
+#define CPET_LAT_CASE(M) (U == 1 ? CPET_LAT_PZ(M, 1) : (U == 4 ? CPET_LAT_PZ(M, 4) : CPET_LAT_PZ(M, 2)))
     if (mode == MODE_FIELD_SOFT) rc = CPET_LAT_CASE(MODE_FIELD_SOFT);
     else if (mode == MODE_FIELD_RAW) rc = CPET_LAT_CASE(MODE_FIELD_RAW);
     else rc = CPET_LAT_CASE(MODE_ESP);
 #undef CPET_LAT_CASE
+#undef CPET_LAT_PZ
     if (rc) return rc;
     c->last_counters[0] = 1;
     c->last_path = 1;

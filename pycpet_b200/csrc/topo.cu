@@ -431,8 +431,13 @@ int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d
     if (G <= 0) {
         // Measured on B200 (profiles/round1_sweep.md): 16 warps/SM are needed to hide latency, and
         // the longest-first queue evens out the tail once there are >= ~2.5 lines per slot.
+        // Long lines (the reference's max_steps = round(2*|dims|/h), SC:272, in the hundreds) leave a
+        // longer, more ragged tail: ask for >= 5 lines per slot there (h = 0.01: +12 %).
+        const double diag = sqrt((double)dims[0] * dims[0] + (double)dims[1] * dims[1] + (double)dims[2] * dims[2]);
+        const double max_steps = step > 0.f ? 2.0 * diag / (double)step : 0.0;
+        const long long per_slot_x2 = max_steps > 32.0 ? 10 : 5;
         G = 1;
-        while (G < 32 && 2LL * n_lines * G < 5LL * sms * threads * P) G *= 2;
+        while (G < 32 && 2LL * n_lines * G < per_slot_x2 * sms * threads * P) G *= 2;
     }
     if (G & (G - 1)) G = 1;
     if (G > 32) G = 32;

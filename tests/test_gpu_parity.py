@@ -377,6 +377,43 @@ def test_topo_streamed_charges_large_frame(M):
     assert per_point.max() < 1e-5, per_point.max()
 
 
+def test_topo_fine_step(M, golden):
+    """h = 0.001 (the finest step of the reference's convergence protocol,
+    scripts/benchmark_sample_step.py:43): thousands of steps per line."""
+    g = golden("synthetic_math_ops.npz")
+    x, Q = g["x"], g["Q"]
+    h = 0.001
+    seeds = g["seeds"][:24]
+    dims = g["dimensions"]
+    max_steps = round(2 * np.linalg.norm(dims) / h)
+    n_iter = np.random.RandomState(42).randint(1, max_steps, len(seeds))
+    want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, h, dims)
+    got, steps = M.topo_batch(seeds, n_iter, x, Q, h, dims, want_steps=True)
+    # step-count flips at the box face are possible after thousands of FP32 steps: compare the rest
+    same = steps == wsteps
+    assert same.mean() >= 0.9
+    assert np.max(np.abs(got[same, 0] - want[same, 0])) <= 2e-5      # accumulated FP32 position rounding
+    assert np.max(np.abs(got[same, 1] - want[same, 1])) <= curv_tol_dir(h)
+    got_sd, steps_sd = M.topo_batch(seeds, n_iter, x, Q, h, dims, second_diff=True, want_steps=True)
+    np.testing.assert_array_equal(steps_sd, steps)
+    assert np.max(np.abs(got_sd[same, 1] - want[same, 1])) <= curv_tol_sd(h)
+    # the direction-based default is orders of magnitude closer to float64 than second differences
+    assert np.max(np.abs(got[same, 1] - want[same, 1])) < 0.1 * np.max(np.abs(got_sd[same, 1] - want[same, 1])) + 1e-4
+
+
+def test_field_one_million_charges(M):
+    """Sweep corner M = 1e6 (16 MB of packed charges streamed from L2 through the TMA ring)."""
+    x, Q = synth.charges(1_000_000, seed=8, box=1.5)
+    pts = synth.grid(4, 1.5)
+    M.set_charges(x, Q)
+    assert relmax(M.field_grid(pts, soften=True), f64.field_grid(pts, x, Q, True)) < FIELD_TOL
+    assert relmax(M.esp_grid(pts), f64.esp_grid(pts, x, Q)) < FIELD_TOL
+    seeds, n_iter, dims, _ = synth.seeds(3, 0.5, 0.1)
+    want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
+    got, steps = M.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, want_steps=True)
+    check_lines(got, steps, want, wsteps, 0.1, curv_tol_field_limited(0.1))
+
+
 def test_topo_edge_cases(M, frame2a):
     x, Q = frame2a
     dims = np.array([0.5, 0.5, 0.5], np.float32)

@@ -19,10 +19,12 @@ x, Q = synth.charges(7890, seed=1, box=0.5)
 eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
 if which in ("all", "k1"):
     pts = torch.from_numpy(synth.grid(101, 0.5)).cuda()
+    ax = torch.linspace(-0.5, 0.5, 101, device="cuda")
     for _ in range(reps):
         eng.field_grid(pts, soften=False)
         eng.field_grid(pts, soften=True)
         eng.esp_grid(pts)
+        eng.field_lattice(ax, ax, ax, soften=True)
 if which in ("all", "k2"):
     seeds, n_iter, dims, _ = synth.seeds(47, 0.5, 0.1)
     sd = torch.from_numpy(seeds).cuda()
