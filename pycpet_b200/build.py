@@ -58,7 +58,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc, "-ccbin", host_cxx] + NVCC_FLAGS + ["-c", s, "-o", o]
+        extra = os.environ.get("CPET_NVCC_EXTRA", "").split()     # e.g. -DCPET_K2_MAXT=768 for experiments
+        cmd = [nvcc, "-ccbin", host_cxx] + NVCC_FLAGS + extra + ["-c", s, "-o", o]
         p = subprocess.run(cmd, capture_output=True, text=True, env=env)
         return s, p.returncode, p.stdout + p.stderr
 

@@ -25,6 +25,9 @@
 namespace cpet {
 
 #define K2_KEYMAX 2048
+#ifndef CPET_K2_MAXT
+#define CPET_K2_MAXT 512
+#endif
 #ifndef CPET_K2_UNROLL
 #define CPET_K2_UNROLL 8
 #endif
@@ -101,7 +104,7 @@ struct LineState {
 };
 
 template <int G, int P, bool SD>
-__global__ void __launch_bounds__(512, 1) k2_topo_kernel(const K2Params prm) {
+__global__ void __launch_bounds__(CPET_K2_MAXT, 1) k2_topo_kernel(const K2Params prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     ChargePair* ring = reinterpret_cast<ChargePair*>(smem_raw + 128);
@@ -424,7 +427,7 @@ int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d
     int threads = tu.k2_threads > 0 ? tu.k2_threads : 512;
     threads = (threads / 32) * 32;
     if (threads < 32) threads = 32;
-    if (threads > 512) threads = 512;
+    if (threads > CPET_K2_MAXT) threads = CPET_K2_MAXT;
     int P = tu.k2_points;
     if (P != 1 && P != 2) P = 1;
     int G = tu.k2_lanes;

@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Multi-GPU check of pycpet_b200.sharding over NCCL (run under torchrun on >= 2 GPUs):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/nccl_check.py
+
+Every rank computes its shard with the CUDA kernels (Engine, device pointers), the results are
+gathered / reduced with NCCL, and rank 0 compares them bit for bit with a single-GPU run of the same
+inputs.  The same sharding functions are exercised on CPU over gloo in tests/test_sharding_gloo.py.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import synth  # noqa: E402
+from pycpet_b200 import sharding  # noqa: E402
+from pycpet_b200.device import Engine  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = Engine(local)
+    # the launch heuristics depend on the shard size (lanes per point/line, charge splits), which
+    # changes the order of the FP64 partial sums; pin them so sharded == unsharded bit for bit
+    eng.set_tuning(k1_lanes=8, k1_splits=1, k2_lanes=8, k2_threads=256)
+    x, Q = synth.charges(7890, seed=1, box=0.5)
+    eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
+
+    # grid points by slabs -> all_gather
+    pts = synth.grid(41, 0.5)
+    field = sharding.grid_sharded(lambda p: eng.field_grid(torch.from_numpy(np.ascontiguousarray(p)).cuda(),
+                                                           soften=True), pts)
+    # one frame's streamlines by an LPT deal -> all_gather + restore seed order
+    seeds, n_iter, dims, _ = synth.seeds(30, 0.5, 0.1)
+    topo = sharding.topo_sharded(
+        lambda s, n: eng.topo_batch(torch.from_numpy(np.ascontiguousarray(s)).cuda(), n, 0.1, dims), seeds, n_iter)
+    # histogram of the lines held by this rank -> all_reduce(sum); global ranges -> all_reduce(min/max)
+    ids = sharding.deal_lines(n_iter, rank, world)
+    mine = topo[torch.as_tensor(ids, device=topo.device)]
+    lo_d, hi_d, lo_c, hi_c = sharding.global_ranges(mine)
+    de, ce = np.linspace(lo_d, hi_d, 41), np.linspace(lo_c, hi_c, 31)
+    counts = sharding.hist_sharded(lambda v, a, b: eng.hist2d(v, a, b), mine, de, ce)
+    # MD frames round-robin -> gather by frame id
+    def frame(f):
+        rng = np.random.default_rng(100 + f)
+        xf = (x + rng.normal(0, 0.3, x.shape)).astype(np.float32)
+        xf[np.all(np.abs(xf) < 0.55, axis=1)] *= 3.0
+        eng.set_charges(torch.from_numpy(xf).cuda(), torch.from_numpy(Q).cuda())
+        rows = eng.topo_batch(torch.from_numpy(seeds[:4096]).cuda(), n_iter[:4096], 0.1, dims)
+        return eng.hist2d(rows, np.linspace(0, 1.8, 51), np.linspace(0, 5, 51)).clone()
+    frames = sharding.frames_sharded(frame, 6)
+    torch.cuda.synchronize()
+
+    ok = True
+    if rank == 0:
+        eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
+        f1 = eng.field_grid(torch.from_numpy(pts).cuda(), soften=True)
+        t1 = eng.topo_batch(torch.from_numpy(seeds).cuda(), n_iter, 0.1, dims)
+        c1 = eng.hist2d(t1, de, ce)
+        fr1 = torch.stack([frame(f) for f in range(6)])
+        checks = {
+            "field all_gather": torch.equal(field, f1),
+            "topo gather + seed order": torch.equal(topo, t1),
+            "global ranges": (lo_d, hi_d, lo_c, hi_c) == (float(t1[:, 0].min()), float(t1[:, 0].max()),
+                                                         float(t1[:, 1].min()), float(t1[:, 1].max())),
+            "hist all_reduce": torch.equal(counts.to(c1.device), c1) and int(counts.sum()) == len(seeds),
+            "frames gather": torch.equal(frames.to(fr1.device).to(fr1.dtype), fr1),
+        }
+        for k, v in checks.items():
+            print(f"[nccl_check world={world}] {k}: {'OK' if v else 'MISMATCH'}")
+            ok = ok and v
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
