@@ -28,6 +28,9 @@ namespace cpet {
 #ifndef CPET_K2_MAXT
 #define CPET_K2_MAXT 512
 #endif
+#ifndef CPET_K2_UNROLL_P2
+#define CPET_K2_UNROLL_P2 2
+#endif
 #ifndef CPET_K2_UNROLL
 #define CPET_K2_UNROLL 8
 #endif
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(CPET_K2_MAXT, 1) k2_topo_kernel(const K2Params
         if (prm.resident) {
             for (int t = 0; t < NT; ++t) {
                 const int n_t = min(TP, prm.n_pairs - t * TP);
-                eval_tile_chunked<MODE_FIELD_RAW, P, (P >= 2 ? 2 : CPET_K2_UNROLL), 64>(ring + (size_t)t * TP, lane_g,
+                eval_tile_chunked<MODE_FIELD_RAW, P, (P >= 2 ? CPET_K2_UNROLL_P2 : CPET_K2_UNROLL), 64>(ring + (size_t)t * TP, lane_g,
                                                                            n_t, G, r, acc);
             }
         } else {
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(CPET_K2_MAXT, 1) k2_topo_kernel(const K2Params
                 mbar_wait(&full[stage], (uint32_t)((it / S) & 1));
                 if (warp_on) {
                     const int n_t = min(TP, prm.n_pairs - t * TP);
-                    eval_tile_chunked<MODE_FIELD_RAW, P, (P >= 2 ? 2 : CPET_K2_UNROLL), 64>(
+                    eval_tile_chunked<MODE_FIELD_RAW, P, (P >= 2 ? CPET_K2_UNROLL_P2 : CPET_K2_UNROLL), 64>(
                         ring + (size_t)stage * TP, lane_g, n_t, G, r, acc);
                 }
                 __syncthreads();                      // stage fully consumed by the CTA
