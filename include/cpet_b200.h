@@ -159,6 +159,21 @@ int cpet_topo_hist(cpet_ctx *ctx, int n_lines, const float *seeds, const int32_t
                    int32_t *steps, int nd, const double *d_edges, int nc, const double *c_edges,
                    int64_t *counts);
 
+/* Exact order statistics of float32 values on the device: out[t] = the ranks[t]-th smallest
+ * (0-based) of values[i*stride + offset], i < n, NaNs ordered last as NumPy sorts them.  Rank 0 and
+ * n-1 give the global min / max, the neighbours of 0.25(n-1) and 0.75(n-1) give scipy.stats.iqr,
+ * i.e. everything make_histograms needs for its bin plan (UC:664-685) without a host sort.
+ * MSB radix select, four 8-bit passes; up to 16 ranks per call.
+ * cpet_radix_hist_dev is the single pass (for every target t: 256-bin histogram of the next 8 key
+ * bits among values whose leading prefix_bits bits equal prefixes[t]); a multi-GPU caller
+ * all-reduces `hist` between passes (pycpet_b200/sharding.py). */
+int cpet_order_stats(cpet_ctx *ctx, int64_t n, const float *values, int stride, int offset,
+                     int n_ranks, const int64_t *ranks, float *out);
+int cpet_order_stats_dev(cpet_ctx *ctx, int64_t n, const float *d_values, int stride, int offset,
+                         int n_ranks, const int64_t *ranks, float *out);
+int cpet_radix_hist_dev(cpet_ctx *ctx, int64_t n, const float *d_values, int stride, int offset,
+                        int n_targets, const uint32_t *prefixes, int prefix_bits, uint64_t *hist);
+
 /* Pairwise chi^2 distance matrix (UC:975-978, UC:1003-1015):
  * out[i][j] = 1/2 sum_{b: h_i[b]+h_j[b] != 0} (h_i[b]-h_j[b])^2 / (h_i[b]+h_j[b]); diagonal 0.
  * H: (n_hists, n_bins) float64 host; out: (n_hists, n_hists) float64 host. */

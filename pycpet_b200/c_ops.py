@@ -252,6 +252,17 @@ class Math_ops:
         check(fn(self.ctx, v.shape[0], v.shape[1], ptr(v), nd, ptr(de), nc, ptr(ce), ptr(counts)))
         return counts[0] if single else counts
 
+    def order_stats(self, values, ranks, column=0):
+        """Exact ranks-th smallest (0-based) entries of column `column` of a float32 (n, k) array
+        (or of a flat array), selected on the device -> float32 array, NaNs ordered last."""
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        stride = 1 if v.ndim == 1 else int(np.prod(v.shape[1:]))
+        n = v.shape[0]
+        r = np.ascontiguousarray(ranks, dtype=np.int64).reshape(-1)
+        out = np.zeros(r.shape[0], dtype=np.float32)
+        check(self.math.cpet_order_stats(self.ctx, n, ptr(v), stride, int(column), r.shape[0], ptr(r), ptr(out)))
+        return out
+
     def chi2_matrix(self, H):
         H = np.ascontiguousarray(H, dtype=np.float64)
         if H.ndim != 2:

@@ -162,6 +162,55 @@ def bin_plan(topologies):
     return d_range, c_range, nd, nc
 
 
+def quartile_ranks(n):
+    """0-based ranks of the order statistics np.percentile(x, [25, 75]) (default 'linear' method)
+    interpolates between, plus the interpolation weights, using NumPy's own virtual-index formula
+    n*q + (alpha + q*(1 - alpha - beta)) - 1 with alpha = beta = 1."""
+    out = []
+    for q in (0.25, 0.75):
+        virtual = n * q + (1 + q * (1 - 1 - 1)) - 1
+        prev = int(np.floor(virtual))
+        out.append((prev, min(prev + 1, n - 1), float(virtual - prev)))
+    return out
+
+
+def _lerp(a, b, t):
+    """numpy.lib._function_base_impl._lerp for scalars (float64)."""
+    a, b = np.float64(a), np.float64(b)
+    d = b - a
+    return b - d * (1 - t) if t >= 0.5 else a + d * t
+
+
+def plan_from_order_stats(stats, n_ref):
+    """(d_range, c_range, nd, nc) from the six order statistics per column
+    [min, q25_lo, q25_hi, q75_lo, q75_hi, max] and the interpolation weights of quartile_ranks."""
+    ranges, nbins = [], []
+    for col in (0, 1):
+        (lo, a25, b25, a75, b75, hi), (g25, g75) = stats[col]
+        iqr = _lerp(a75, b75, g75) - _lerp(a25, b25, g25)
+        res = 2 * iqr / (n_ref ** (1 / 3))
+        lo, hi = float(np.float64(lo)), float(np.float64(hi))
+        ranges.append((lo, hi))
+        nbins.append(int((hi - lo) / res))
+    return ranges[0], ranges[1], nbins[0], nbins[1]
+
+
+def bin_plan_device(topologies):
+    """bin_plan() with the global min / max and the exact inter-quartile range taken from
+    device-side radix selection (no host sort): same return value as bin_plan(), bit for bit.
+    topologies: (F, n, 2) float32 array or a list of (n_i, 2) float32 arrays."""
+    tops = [np.ascontiguousarray(t, dtype=np.float32).reshape(-1, 2) for t in topologies]
+    lens = np.array([len(t) for t in tops])
+    n_ref = lens[0] if np.all(lens == lens[0]) else np.mean(lens)
+    allv = np.concatenate(tops) if len(tops) > 1 else tops[0]
+    n = len(allv)
+    (p25, n25, g25), (p75, n75, g75) = quartile_ranks(n)
+    ranks = [0, p25, n25, p75, n75, n - 1]
+    m = get_math()
+    stats = [(tuple(m.order_stats(allv, ranks, column=c).tolist()), (g25, g75)) for c in (0, 1)]
+    return plan_from_order_stats(stats, n_ref)
+
+
 def make_histograms_from_arrays(topologies, plan=None):
     """Histograms of a list of (n_i,2) [dist|curv] arrays -> (F, nd*nc) float64, each row
     a/a.sum() flattened row-major (UC:702-713).  Frames of equal length go to the GPU as one

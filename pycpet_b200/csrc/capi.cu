@@ -542,6 +542,85 @@ int cpet_topo_hist(cpet_ctx* c, int n_lines, const float* seeds, const int32_t* 
     return CPET_OK;
 }
 
+// ---------------------------------------------------------------- order statistics ----------
+int cpet_radix_hist_dev(cpet_ctx* c, int64_t n, const float* d_values, int stride, int offset, int n_targets,
+                        const uint32_t* prefixes, int prefix_bits, uint64_t* hist) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n >= 0 && stride >= 1 && offset >= 0 && offset < stride, CPET_ERR_INVALID, "bad value layout");
+    CPET_REQUIRE(prefixes && hist && (n == 0 || d_values), CPET_ERR_INVALID, "NULL arrays");
+    CPET_REQUIRE(n_targets >= 1 && n_targets <= 16, CPET_ERR_INVALID, "1..16 targets per pass");
+    const size_t hb = sizeof(unsigned long long) * 256 * (size_t)n_targets;
+    if (int rc = c->work2.reserve(hb + 64)) return rc;
+    unsigned* d_pre = c->work2.as<unsigned>();
+    unsigned long long* d_hist = reinterpret_cast<unsigned long long*>(c->work2.as<unsigned char>() + 64);
+    CPET_CUDA_TRY(cudaMemcpyAsync(d_pre, prefixes, sizeof(unsigned) * n_targets, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = launch_radix_hist(c, n, d_values, stride, offset, n_targets, d_pre, prefix_bits, d_hist)) return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(hist, d_hist, hb, cudaMemcpyDeviceToHost, c->stream));
+    CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPET_OK;
+}
+
+static int order_stats_impl(cpet_ctx* c, int64_t n, const float* d_values, int stride, int offset, int n_ranks,
+                            const int64_t* ranks, float* out) {
+    CPET_REQUIRE(n_ranks >= 1 && n_ranks <= 16, CPET_ERR_INVALID, "1..16 ranks per call");
+    CPET_REQUIRE(n >= 1, CPET_ERR_INVALID, "order statistics of an empty array");
+    int64_t k[16];
+    uint32_t prefix[16];
+    std::vector<uint64_t> hist(256 * 16);
+    for (int t = 0; t < n_ranks; ++t) {
+        CPET_REQUIRE(ranks[t] >= 0 && ranks[t] < n, CPET_ERR_INVALID, "rank %lld out of range", (long long)ranks[t]);
+        k[t] = ranks[t];
+        prefix[t] = 0;
+    }
+    int launches = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        // pass 0 has no prefix yet: one shared histogram serves every target
+        const int nt = pass == 0 ? 1 : n_ranks;
+        if (int rc = cpet_radix_hist_dev(c, n, d_values, stride, offset, nt, prefix, 8 * pass, hist.data())) return rc;
+        ++launches;
+        for (int t = 0; t < n_ranks; ++t) {
+            const uint64_t* h = hist.data() + 256 * (pass == 0 ? 0 : t);
+            uint64_t cum = 0;
+            int b = 0;
+            for (; b < 256; ++b) {
+                if ((uint64_t)k[t] < cum + h[b]) break;
+                cum += h[b];
+            }
+            CPET_REQUIRE(b < 256, CPET_ERR_STATE, "radix select lost rank %d (values changed between passes?)", t);
+            k[t] -= (int64_t)cum;
+            prefix[t] = (prefix[t] << 8) | (uint32_t)b;
+        }
+    }
+    for (int t = 0; t < n_ranks; ++t) {
+        const uint32_t key = prefix[t];
+        const uint32_t u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+        memcpy(&out[t], &u, sizeof(float));
+    }
+    c->last_counters[0] = launches;
+    c->last_counters[1] = 0;
+    c->last_counters[2] = 0;
+    return CPET_OK;
+}
+
+int cpet_order_stats_dev(cpet_ctx* c, int64_t n, const float* d_values, int stride, int offset, int n_ranks,
+                         const int64_t* ranks, float* out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(d_values && ranks && out, CPET_ERR_INVALID, "NULL arrays");
+    CPET_REQUIRE(stride >= 1 && offset >= 0 && offset < stride, CPET_ERR_INVALID, "bad value layout");
+    return order_stats_impl(c, n, d_values, stride, offset, n_ranks, ranks, out);
+}
+
+int cpet_order_stats(cpet_ctx* c, int64_t n, const float* values, int stride, int offset, int n_ranks,
+                     const int64_t* ranks, float* out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(values && ranks && out, CPET_ERR_INVALID, "NULL arrays");
+    CPET_REQUIRE(n >= 1 && stride >= 1 && offset >= 0 && offset < stride, CPET_ERR_INVALID, "bad value layout");
+    const size_t bytes = sizeof(float) * (size_t)n * stride;
+    if (int rc = c->in0.reserve(bytes)) return rc;
+    CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, values, bytes, cudaMemcpyHostToDevice, c->stream));
+    return order_stats_impl(c, n, c->in0.as<float>(), stride, offset, n_ranks, ranks, out);
+}
+
 int cpet_chi2_matrix(cpet_ctx* c, int n_hists, int64_t n_bins, const double* H, double* out) {
     CTX_GUARD(c);
     CPET_REQUIRE(n_hists >= 0 && n_bins >= 0, CPET_ERR_INVALID, "negative sizes");

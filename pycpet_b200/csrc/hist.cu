@@ -113,6 +113,65 @@ int launch_hist2d(cpet_ctx* c, int n_frames, int64_t n_per_frame, const void* d_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Radix-select building block for exact order statistics (global min / max and the 25th / 75th
+// percentile neighbours that make_histograms' bin widths need: UC:664-670, scipy.stats.iqr).
+// One pass = for every target t, the 256-bin histogram of the next 8 key bits over the values
+// whose leading `prefix_bits` bits equal prefixes[t].  Keys are the usual monotone map of float32
+// (all NaNs last, as NumPy sorts them).  Four passes pin any rank exactly; the pass loop lives on
+// the host (and all-reduces the histograms across ranks for multi-GPU selection).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned monotone_key(float v) {
+    if (v != v) return 0xffffffffu;
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+#define CPET_RADIX_MAX_TARGETS 16
+
+__global__ void __launch_bounds__(256) radix_hist_kernel(const float* __restrict__ values, long long n,
+                                                         int stride, int offset, int n_targets,
+                                                         const unsigned* __restrict__ prefixes,
+                                                         int prefix_bits,
+                                                         unsigned long long* __restrict__ hist) {
+    __shared__ unsigned cnt[CPET_RADIX_MAX_TARGETS][256];
+    __shared__ unsigned pre[CPET_RADIX_MAX_TARGETS];
+    for (int i = threadIdx.x; i < n_targets * 256; i += blockDim.x) cnt[i >> 8][i & 255] = 0u;
+    if (threadIdx.x < n_targets) pre[threadIdx.x] = prefixes[threadIdx.x];
+    __syncthreads();
+    const int shift = 24 - prefix_bits;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const unsigned key = monotone_key(values[i * stride + offset]);
+        const unsigned head = prefix_bits ? (key >> (32 - prefix_bits)) : 0u;
+        const unsigned bin = (key >> shift) & 255u;
+        for (int t = 0; t < n_targets; ++t)
+            if (prefix_bits == 0 || head == pre[t]) atomicAdd(&cnt[t][bin], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_targets * 256; i += blockDim.x)
+        if (cnt[i >> 8][i & 255]) atomicAdd(&hist[i], (unsigned long long)cnt[i >> 8][i & 255]);
+}
+
+int launch_radix_hist(cpet_ctx* c, long long n, const float* d_values, int stride, int offset,
+                      int n_targets, const unsigned* d_prefixes, int prefix_bits,
+                      unsigned long long* d_hist) {
+    CPET_REQUIRE(n_targets >= 1 && n_targets <= CPET_RADIX_MAX_TARGETS, CPET_ERR_INVALID,
+                 "radix select handles 1..%d targets per pass", CPET_RADIX_MAX_TARGETS);
+    CPET_REQUIRE(prefix_bits == 0 || prefix_bits == 8 || prefix_bits == 16 || prefix_bits == 24,
+                 CPET_ERR_INVALID, "prefix_bits must be 0, 8, 16 or 24");
+    CPET_CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 256 * n_targets, c->stream));
+    c->last_counters[0] = 0;
+    if (n <= 0) return CPET_OK;
+    long long blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > (long long)c->sm_count * 8) blocks = (long long)c->sm_count * 8;
+    radix_hist_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(d_values, n, stride, offset, n_targets,
+                                                              d_prefixes, prefix_bits, d_hist);
+    CPET_CUDA_TRY(cudaGetLastError());
+    c->last_counters[0] = 1;
+    return CPET_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // chi^2 distance matrix: one CTA per (i, j>i) pair, FP64.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) chi2_kernel(const double* __restrict__ H, int n,

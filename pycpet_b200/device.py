@@ -168,6 +168,27 @@ class Engine:
         self._keep2 = (seeds, n_iter)
         return (out, steps) if want_steps else out
 
+    def radix_hist(self, values, column, prefixes, prefix_bits):
+        """One radix-select pass over column `column` of a float32 CUDA tensor (n, k):
+        -> (len(prefixes), 256) uint64 histogram of the next 8 key bits (host array)."""
+        v = self._f32(values)
+        stride = 1 if v.dim() == 1 else int(v.shape[1])
+        pre = np.ascontiguousarray(prefixes, dtype=np.uint32).reshape(-1)
+        hist = np.zeros((pre.shape[0], 256), dtype=np.uint64)
+        check(self.lib.cpet_radix_hist_dev(self.ctx, int(v.shape[0]), _p(v), stride, int(column), pre.shape[0],
+                                           _lib.ptr(pre), int(prefix_bits), _lib.ptr(hist)))
+        return hist
+
+    def order_stats(self, values, ranks, column=0):
+        """Exact ranks-th smallest entries (0-based) of a float32 CUDA tensor column -> float32 ndarray."""
+        v = self._f32(values)
+        stride = 1 if v.dim() == 1 else int(v.shape[1])
+        r = np.ascontiguousarray(ranks, dtype=np.int64).reshape(-1)
+        out = np.zeros(r.shape[0], dtype=np.float32)
+        check(self.lib.cpet_order_stats_dev(self.ctx, int(v.shape[0]), _p(v), stride, int(column), r.shape[0],
+                                            _lib.ptr(r), _lib.ptr(out)))
+        return out
+
     def hist2d(self, values, d_edges, c_edges, out=None):
         """values: (F, n, 2) or (n, 2) float32 CUDA tensor -> (F, nd, nc) / (nd, nc) int64."""
         torch = self.torch

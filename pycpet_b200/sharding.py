@@ -169,6 +169,34 @@ def global_ranges(values_local):
     return float(lo[0]), float(hi[0]), float(lo[1]), float(hi[1])
 
 
+def order_stats_sharded(radix_hist, ranks):
+    """Exact global order statistics of values spread over the ranks (the
+    global min/max + IQR of make_histograms over every line of every frame without gathering them).
+    radix_hist(prefixes, prefix_bits) -> (len(prefixes), 256) histogram of THIS rank's values
+    (Engine.radix_hist bound to the local tensor); the histograms are all-reduced after each of the
+    four 8-bit passes, so every rank walks the same prefixes.  Returns float32 values."""
+    import torch
+
+    ranks = [int(r) for r in ranks]
+    k = list(ranks)
+    prefix = [0] * len(ranks)
+    for p in range(4):
+        pre = [0] if p == 0 else prefix
+        h = np.asarray(radix_hist(np.asarray(pre, dtype=np.uint32), 8 * p)).astype(np.int64)
+        h = all_reduce_(torch.from_numpy(np.ascontiguousarray(h)), "sum").cpu().numpy()
+        for t in range(len(ranks)):
+            row = h[0 if p == 0 else t]
+            cum = np.concatenate([[0], np.cumsum(row)])
+            b = int(np.searchsorted(cum, k[t], side="right") - 1)
+            if b > 255:
+                raise ValueError("rank beyond the number of values")
+            k[t] -= int(cum[b])
+            prefix[t] = (prefix[t] << 8) | b
+    keys = np.asarray(prefix, dtype=np.uint32)
+    bits = np.where(keys & np.uint32(0x80000000), keys & np.uint32(0x7FFFFFFF), ~keys)
+    return bits.astype(np.uint32).view(np.float32)
+
+
 def frames_sharded(compute_frame, n_frames):
     """MD-frame batch: this rank runs compute_frame(f) for f = rank, rank+size, ...; the per-frame
     results (equal-shaped arrays/tensors) are gathered and returned stacked in frame order."""

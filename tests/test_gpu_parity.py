@@ -172,8 +172,13 @@ def test_field_full_size_properties(M):
     x, Q = synth.charges(20_000, seed=4, box=5.0)
     pts = synth.grid(101, 5.0)
     assert len(pts) == 101 ** 3
+    # the mesh goes to the lattice kernel, its permutation to the general one: with the charge range
+    # unsplit both add the same FP64 partials in the same order, so the comparison is bit for bit
+    reset_tuning(M)
+    M.set_tuning(k1_splits=1)
     M.set_charges(x, Q)
     e = M.field_grid(pts, soften=True)
+    assert M.last_path() == "lattice"
     M.set_charges(x, 2.0 * Q)
     e2 = M.field_grid(pts, soften=True)
     np.testing.assert_array_equal(e2, 2.0 * e)                      # bit-exact scaling
@@ -181,7 +186,9 @@ def test_field_full_size_properties(M):
     perm = rng.permutation(len(pts))
     M.set_charges(x, Q)
     ep = M.field_grid(pts[perm], soften=True)
+    assert M.last_path() == "general"
     np.testing.assert_array_equal(ep, e[perm])                      # per-point independence
+    reset_tuning(M)
     idx = rng.choice(len(pts), 2000, replace=False)
     assert relmax(e[idx], f64.field_grid(pts[idx], x, Q, True)) < FIELD_TOL
     phi = M.esp_grid(pts)
@@ -493,6 +500,64 @@ def test_hist2d_edges_nan_batch(M):
     assert got.sum() == 5 * 4001
     # empty input
     assert M.hist2d(np.zeros((0, 2)), ed, ed).sum() == 0
+
+
+def test_order_stats_and_device_bin_plan(M):
+    """Exact order statistics by device radix select, and the make_histograms bin plan built on
+    them (global min/max + scipy.stats.iqr), against NumPy/SciPy on the host."""
+    from pycpet_b200 import calculator as calc
+
+    rng = np.random.default_rng(21)
+    v = np.concatenate([rng.normal(0, 1, 50_000), rng.gamma(2.0, 0.3, 50_000), [0.0, -0.0, 1e-40, -1e-40],
+                        np.full(100, 0.5), [np.inf, -np.inf]]).astype(np.float32)
+    rng.shuffle(v)
+    s = np.sort(v)
+    ranks = np.array([0, 1, 17, len(v) // 4, len(v) // 2, 3 * len(v) // 4, len(v) - 2, len(v) - 1])
+    got = M.order_stats(v, ranks)
+    np.testing.assert_array_equal(got, s[ranks])
+    # NaNs are ordered last, like np.sort
+    vn = v.copy()
+    vn[::1000] = np.nan
+    sn = np.sort(vn)
+    got = M.order_stats(vn, [0, len(vn) // 2, len(vn) - 150, len(vn) - 1])
+    np.testing.assert_array_equal(got, sn[[0, len(vn) // 2, len(vn) - 150, len(vn) - 1]])
+    # strided columns of an (n,2) array
+    two = np.column_stack([v, -v]).astype(np.float32)
+    np.testing.assert_array_equal(M.order_stats(two, [5, 100], column=1), np.sort(-v)[[5, 100]])
+    # single element
+    np.testing.assert_array_equal(M.order_stats(np.array([3.5], np.float32), [0]), [3.5])
+    # the bin plan of make_histograms (UC:664-685)
+    for n_frames, n in [(1, 5832), (4, 5832), (3, 1000)]:
+        tops = [np.column_stack([rng.gamma(2.0 + 0.1 * i, 0.3, n), rng.gamma(1.5, 0.4, n)]).astype(np.float32)
+                for i in range(n_frames)]
+        assert calc.bin_plan_device(tops) == calc.bin_plan(tops)
+
+
+def test_radix_pass_matches_numpy_twin():
+    """Engine.radix_hist (the single select pass a multi-GPU caller all-reduces) against the NumPy
+    twin used by the gloo test, and sharding.order_stats_sharded driven by the device pass."""
+    import torch
+
+    from pycpet_b200 import sharding
+    from pycpet_b200.device import Engine
+    from test_sharding_gloo import np_radix_hist
+
+    rng = np.random.default_rng(5)
+    v = np.column_stack([rng.gamma(2.0, 0.3, 20_001), rng.normal(0, 2, 20_001)]).astype(np.float32)
+    v[7, 1] = np.nan
+    eng = Engine(0)
+    dv = torch.from_numpy(v).cuda()
+    for col in (0, 1):
+        h0 = eng.radix_hist(dv, col, [0], 0)
+        np.testing.assert_array_equal(h0, np_radix_hist(v[:, col], [0], 0))
+        top = int(np.argmax(h0[0]))
+        for bits, pre in ((8, [top, (top + 1) % 256]), (16, [top << 8 | 3, top << 8 | 200])):
+            np.testing.assert_array_equal(eng.radix_hist(dv, col, pre, bits), np_radix_hist(v[:, col], pre, bits))
+        ranks = [0, 5000, 10_000, 20_000]
+        got = sharding.order_stats_sharded(lambda pre, bits: eng.radix_hist(dv, col, pre, bits), ranks)
+        np.testing.assert_array_equal(got, np.sort(v[:, col])[ranks])
+        np.testing.assert_array_equal(eng.order_stats(dv, ranks, column=col), np.sort(v[:, col])[ranks])
+    eng.close()
 
 
 def test_make_histograms_and_chi2(M, tmp_path):

@@ -35,3 +35,28 @@ def test_partitioners():
     np.testing.assert_array_equal(allids, np.arange(1000))
     work = [n_iter[p].sum() for p in parts]
     assert max(work) / min(work) < 1.05
+
+
+def test_plan_from_order_stats_reproduces_numpy_scipy():
+    """The bin plan computed from six order statistics per column (what the device radix select
+    returns) equals make_histograms' np.min/np.max/scipy.stats.iqr route bit for bit."""
+    rng = np.random.default_rng(11)
+    for n_frames, n in [(1, 10), (3, 1000), (2, 5832), (5, 777), (1, 2)]:
+        tops = [np.column_stack([rng.gamma(2.0, 0.3, n), rng.gamma(1.5, 0.4, n)]).astype(np.float32)
+                for _ in range(n_frames)]
+        allv = np.concatenate(tops)
+        N = len(allv)
+        (p25, n25, g25), (p75, n75, g75) = calc.quartile_ranks(N)
+        stats = []
+        for col in (0, 1):
+            s = np.sort(allv[:, col])
+            stats.append(((s[0], s[p25], s[n25], s[p75], s[n75], s[-1]), (g25, g75)))
+        got = calc.plan_from_order_stats(stats, n)
+        if got[2] > 0 and got[3] > 0:
+            assert got == calc.bin_plan(tops)
+        # the quartiles themselves against numpy
+        for col in (0, 1):
+            (lo, a25, b25, a75, b75, hi), _ = stats[col]
+            x64 = allv[:, col].astype(np.float64)
+            assert calc._lerp(a25, b25, g25) == np.percentile(x64, 25)
+            assert calc._lerp(a75, b75, g75) == np.percentile(x64, 75)

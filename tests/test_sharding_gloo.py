@@ -21,6 +21,19 @@ def _free_port():
     return p
 
 
+def np_radix_hist(values, prefixes, prefix_bits):
+    """NumPy twin of radix_hist_kernel (hist.cu): monotone float32 keys, NaNs last."""
+    u = np.ascontiguousarray(values, dtype=np.float32).view(np.uint32)
+    key = np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000)).astype(np.uint32)
+    key[np.isnan(values)] = np.uint32(0xFFFFFFFF)
+    out = np.zeros((len(prefixes), 256), dtype=np.uint64)
+    for t, pre in enumerate(prefixes):
+        sel = key if prefix_bits == 0 else key[(key >> np.uint32(32 - prefix_bits)) == np.uint32(pre)]
+        bins = (sel >> np.uint32(24 - prefix_bits)) & np.uint32(255)
+        out[t] = np.bincount(bins.astype(np.int64), minlength=256)
+    return out
+
+
 def _worker(rank, size, port, tmp):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -46,8 +59,13 @@ def _worker(rank, size, port, tmp):
         lambda v, a, b: ohist.hist2d_counts(v[:, 0], v[:, 1], 7, 5, (a[0], a[-1]), (b[0], b[-1])),
         ref_topo[ids], de, ce).numpy()
     frames = sharding.frames_sharded(lambda f: np.full((2, 3), float(f)), 5).numpy()
+    # exact global order statistics of values spread over the ranks (radix select + all-reduce)
+    mine32 = ref_topo[ids][:, 1].astype(np.float32)
+    n_all = len(ref_topo)
+    stats = sharding.order_stats_sharded(lambda pre, bits: np_radix_hist(mine32, pre, bits),
+                                         [0, n_all // 4, n_all // 2, (3 * n_all) // 4, n_all - 1])
     np.savez(os.path.join(tmp, f"r{rank}.npz"), field=full_field, topo=full_topo, counts=counts,
-             frames=frames, ranges=np.array([lo_d, hi_d, lo_c, hi_c]))
+             frames=frames, ranges=np.array([lo_d, hi_d, lo_c, hi_c]), stats=stats)
     dist.destroy_process_group()
 
 
@@ -72,3 +90,6 @@ def test_world_size_2_gloo(tmp_path):
         np.testing.assert_array_equal(z["counts"], expect)
         assert z["counts"].sum() == len(topo)
         np.testing.assert_array_equal(z["frames"][:, 0, 0], np.arange(5.0))
+        srt = np.sort(topo[:, 1].astype(np.float32))
+        n_all = len(srt)
+        np.testing.assert_array_equal(z["stats"], srt[[0, n_all // 4, n_all // 2, (3 * n_all) // 4, n_all - 1]])
