@@ -41,6 +41,14 @@ FLOPS_PER_PAIR = 20.0            # BASELINE.json north_star: "counted at 20 flop
 ESP_FLOPS_PER_PAIR = 11.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.5: 148 SM x 128 lanes x 2 x 1.965 GHz
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
+# `ncu --set full` capture summarised in profiles/round1_ncu_summary.md (same inputs as the bench)
+NCU_TRAFFIC = {
+    "topo3a": (2236416, "profiles/round1_ncu_summary.md k2_topo_kernel<2,1,0>: 2.24 MB read + 0 B written back "
+                        "during the kernel (seeds 12 B + n_iter 4 B + queue order 4 B per line; the 8 B/line "
+                        "output is still in L2 when the kernel ends)"),
+}
+
 WORKLOADS = {
     # name: (kind, description, params)
     "topo3a": ("topo", "3A_field-topology: topo, 47^3=103,823 streamlines, 7,890 synthetic protein-like "
@@ -352,7 +360,10 @@ def run_gpu(args, rank, world, local_rank):
                                     f"FFMA2 {peak_ffma2:.1f} / FFMA {peak_ffma:.1f} TFLOP/s); "
                                     "MEASURED_PEAKS.json has no FP32 entry",
                      "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_nominal": achieved / NOMINAL_FP32_TFLOPS,
-                     "flops_per_pair": flops, "kernel_ms": k_ms, "traffic": None},
+                     "flops_per_pair": flops, "kernel_ms": k_ms,
+                     "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0],
+                     "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1],
+                     "algorithmic_bytes": int(work["units"]) * (28 if kind == "topo" else (36 if kind == "field" else 20))},
     }
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(kind, prm, inp, budget_s=args.cpu_seconds)
@@ -455,6 +466,14 @@ def main():
         return 0
 
     args.warmup = max(args.warmup, 3)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # launched by hand as `python bench.py --gpus N`: start one rank per GPU ourselves, the way
+        # the driver does
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
     import torch
     import torch.distributed as dist
 
