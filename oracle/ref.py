@@ -12,8 +12,6 @@ from __future__ import annotations
 
 import ctypes
 import os
-import threading
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -119,25 +117,52 @@ def thread_operation(seed, n_iter, x, Q, step_size, dimensions) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------------------------
-# Whole-workload drivers (what the reference's calculator-level entry points do), threaded.
-# ctypes drops the GIL during each call and the C functions only touch stack locals in this
-# (non-OpenMP) build, so host threads stand in for the reference's multiprocessing.Pool
-# (CPET/source/calculator.py:690-704) without the pickling cost.
+# Whole-workload drivers (what the reference's calculator-level entry points do).
+# Parallelism = forked worker PROCESSES, exactly the reference's model (multiprocessing.Pool,
+# CPET/source/calculator.py:690-704) -- Python threads would serialise on the GIL around every
+# per-line ctypes call and under-report the reference by ~3x.  Workers inherit the inputs by fork
+# and write results straight into an anonymous shared mapping, so nothing is pickled but the spans.
 # ---------------------------------------------------------------------------------------------
+_WORK = None
+
+
+def _call_work(span):
+    _WORK(*span)
+    return span[1] - span[0]
+
+
+def _shared(shape, dtype):
+    """ndarray backed by MAP_SHARED|MAP_ANONYMOUS memory: children forked later write into it."""
+    import mmap
+
+    nbytes = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
+    buf = mmap.mmap(-1, nbytes)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
 def _run_chunks(fn, n, threads):
+    global _WORK
     threads = max(1, int(threads))
     if threads == 1 or n < 2:
         fn(0, n)
         return
-    # the C code keeps 16-28 bytes of VLA per charge on the stack (C:259-263, 300-307, 409-410)
-    threading.stack_size(256 * 1024 * 1024)
+    import multiprocessing as mp
+    import resource
+
+    try:    # the C code keeps 16-28 bytes of VLA per charge on the stack (C:259-263, 300-307, 409-410)
+        soft, hard = resource.getrlimit(resource.RLIMIT_STACK)
+        resource.setrlimit(resource.RLIMIT_STACK, (hard, hard))
+    except (ValueError, OSError):
+        pass
+    step = max(1, -(-n // (threads * 8)))
+    spans = [(s, min(n, s + step)) for s in range(0, n, step)]
+    _WORK = fn
     try:
-        step = max(1, -(-n // (threads * 8)))
-        spans = [(s, min(n, s + step)) for s in range(0, n, step)]
-        with ThreadPoolExecutor(max_workers=threads) as ex:
-            list(ex.map(lambda ab: fn(*ab), spans))
+        with mp.get_context("fork").Pool(threads) as pool:
+            done = sum(pool.imap_unordered(_call_work, spans))
+        assert done == n
     finally:
-        threading.stack_size(0)
+        _WORK = None
 
 
 def topo(seeds, n_iter, x, Q, step_size, dimensions, threads: int = 1) -> np.ndarray:
@@ -149,7 +174,7 @@ def topo(seeds, n_iter, x, Q, step_size, dimensions, threads: int = 1) -> np.nda
     x, Q = _prep(x, Q)
     L = lib()
     m = Q.shape[0]
-    out = np.zeros((seeds.shape[0], 2), dtype=np.float32)
+    out = _shared((seeds.shape[0], 2), np.float32) if threads > 1 else np.zeros((seeds.shape[0], 2), np.float32)
     h = float(step_size)
 
     def work(a, b):
@@ -166,7 +191,7 @@ def field_grid(x0, x, Q, threads: int = 1) -> np.ndarray:
     x0 = np.ascontiguousarray(x0, dtype=np.float32).reshape(-1, 3)
     x, Q = _prep(x, Q)
     L = lib()
-    out = np.zeros_like(x0)
+    out = _shared(x0.shape, np.float32) if threads > 1 else np.zeros_like(x0)
 
     def work(a, b):
         L.compute_looped_field(b - a, Q.shape[0], x0[a:b], x, Q, out[a:b])
@@ -183,7 +208,7 @@ def esp_grid(x0, x, Q, threads: int = 1) -> np.ndarray:
     x, Q = _prep(x, Q)
     L = lib()
     m = Q.shape[0]
-    out = np.zeros(x0.shape[0], dtype=np.float64)
+    out = _shared((x0.shape[0],), np.float64) if threads > 1 else np.zeros(x0.shape[0], dtype=np.float64)
 
     def work(a, b):
         for i in range(a, b):
