@@ -179,6 +179,14 @@ int cpet_radix_hist_dev(cpet_ctx *ctx, int64_t n, const float *d_values, int str
  * H: (n_hists, n_bins) float64 host; out: (n_hists, n_hists) float64 host. */
 int cpet_chi2_matrix(cpet_ctx *ctx, int n_hists, int64_t n_bins, const double *H, double *out);
 
+/* ---------------------------------------------------------------- text outputs ------------- */
+/* Byte-compatible replacement for the np.savetxt calls that write the path's results: `.top`
+ * (TOP:123, default "%.18e") and the body of `_efield.dat` / `_esp.dat` (IO:98-102, "%.3f"; the
+ * 7-line header IO:59-85 is passed in `header`).  Host code, all cores; dtype 0 = float32,
+ * 1 = float64, 2 = float16; rows are space separated, '\n' terminated. */
+int cpet_write_rows(const char *path, const char *header, const void *data, int dtype,
+                    int64_t n_rows, int n_cols, const char *fmt, int n_threads);
+
 /* ---------------------------------------------------------------- measurement -------------- */
 /* Sustained non-tensor FP32 rate of this device from a register-resident FMA loop.
  * packed=0: FFMA, packed=1: FFMA2 (fma.rn.f32x2).  Returns TFLOP/s in *tflops (2 flop/FMA). */

@@ -1,0 +1,61 @@
+"""Writers for the path's output files, byte-compatible with the reference's np.savetxt calls.
+
+* ``save_topology(path, hist)``         == ``np.savetxt(path, hist)``            (CPET/source/CPET.py:123)
+* ``save_numpy_as_dat(meta, volume, name)`` == CPET/utils/io.py:50-109 (same signature, same bytes)
+
+np.savetxt formats row by row in Python; for a 1,000,000-line `.top` that costs seconds, i.e. two
+orders of magnitude more than computing the lines on the GPU.  ``cpet_write_rows`` does the same
+conversion with snprintf on all host cores.  The 7-line `.dat` header is built here in Python with
+the reference's own format strings (it prints NumPy scalars, whose repr is Python's).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+_DTYPES = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.float16): 2}
+
+
+def write_rows(path, array, fmt="%.18e", header="", threads=0):
+    """Write a 2-D (or 1-D) float array as text, one row per line, space separated."""
+    a = np.asarray(array)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    if a.ndim != 2:
+        raise ValueError("write_rows expects a 1-D or 2-D array")
+    if a.dtype not in _DTYPES:
+        a = a.astype(np.float64)
+    a = np.ascontiguousarray(a)
+    check(_lib.load().cpet_write_rows(os.fsencode(path), header.encode(), _lib.ptr(a), _DTYPES[a.dtype],
+                                      a.shape[0], a.shape[1], fmt.encode(), int(threads)))
+
+
+def save_topology(path, hist):
+    """`.top` file: two columns dist, curv in '%.18e' -- the bytes np.savetxt(path, hist) writes."""
+    write_rows(path, hist, fmt="%.18e")
+
+
+def dat_header(meta_data):
+    """The 7 header lines of `_efield.dat` / `_esp.dat` (CPET/utils/io.py:59-85)."""
+    dimensions = meta_data["dimensions"]
+    num_steps_list = meta_data["num_steps"]
+    trans_mat = meta_data["transformation_matrix"].transpose()
+    center = meta_data["center"]
+    first_line = "#Sample Density: {} {} {}; Volume: Box: {} {} {}\n".format(
+        num_steps_list[0], num_steps_list[1], num_steps_list[2], dimensions[0], dimensions[1], dimensions[2])
+    second_line = "#Frame 0\n"
+    third_line = "#Center: {} {} {}\n".format(center[0], center[1], center[2])
+    basis = "#Basis Matrix:\n# {} {} {}\n# {} {} {}\n# {} {} {}\n".format(
+        trans_mat[0][0], trans_mat[0][1], trans_mat[0][2], trans_mat[1][0], trans_mat[1][1], trans_mat[1][2],
+        trans_mat[2][0], trans_mat[2][1], trans_mat[2][2])
+    return first_line + second_line + third_line + basis
+
+
+def save_numpy_as_dat(meta_data, volume, name):
+    """Same signature and same bytes as the reference's save_numpy_as_dat (CPET/utils/io.py:50-109):
+    header + np.savetxt(name, volume, fmt='%.3f')."""
+    write_rows(name, volume, fmt="%.3f", header=dat_header(meta_data))
