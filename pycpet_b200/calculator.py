@@ -289,4 +289,16 @@ def patch_reference():
     cls.compute_topo_complete_c_shared = compute_topo_complete_c_shared
     cls.compute_topo_GPU_batch_filter = compute_topo_GPU_batch_filter
     cls.compute_point_field = compute_point_field
+    # the `.dat` writer (CPET/utils/io.py:50-109), also where CPET.py imported it by name
+    try:
+        import CPET.source.CPET as TOP  # noqa: N811
+        import CPET.utils.io as IO      # noqa: N811
+
+        from .io import save_numpy_as_dat
+
+        IO.save_numpy_as_dat = save_numpy_as_dat
+        if hasattr(TOP, "save_numpy_as_dat"):
+            TOP.save_numpy_as_dat = save_numpy_as_dat
+    except ImportError:
+        pass
     return cls

@@ -171,3 +171,43 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_dropin_goldens():
+    """Outputs of the UNMODIFIED `CPET(options).run()` on one shipped PDB, for the drop-in test
+    (tests/test_gpu_dropin.py): `volume` -> *_efield.dat, `topo` (seeded) -> *.top."""
+    import gzip
+    import shutil
+    import tempfile
+
+    os.environ["CPET_BANNER"] = "0"
+    install_stubs()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from CPET.source.CPET import CPET
+
+    ex = os.path.join(REF, "examples")
+    pdb = os.path.join(ex, "1A_point-field", "pdb", "1_alcdehydro_run1.pdb")
+    with open(pdb, "rb") as fi, gzip.open(os.path.join(OUT, "1_alcdehydro_run1.pdb.gz"), "wb", compresslevel=9) as fo:
+        shutil.copyfileobj(fi, fo)
+    work = tempfile.mkdtemp()
+    os.makedirs(os.path.join(work, "pdb"))
+    shutil.copy(pdb, os.path.join(work, "pdb"))
+    for name, method, extra in [("2A_3D-field", "volume", {}),
+                                ("3A_field-topology", "topo", {"n_samples": 200, "max_streamline_init": "fixed_rand",
+                                                               "concur_slip": 4})]:
+        opts = json.load(open(os.path.join(ex, name, "options", "options.json")))
+        opts.update(extra)
+        opts["inputpath"] = os.path.join(work, "pdb")
+        opts["outputpath"] = os.path.join(work, "out_" + method)
+        json.dump({k: v for k, v in opts.items() if k not in ("inputpath", "outputpath")},
+                  open(os.path.join(OUT, f"dropin_options_{method}.json"), "w"), indent=1)
+        CPET(opts).run()
+        produced = sorted(os.listdir(opts["outputpath"]))
+        assert len(produced) == 1, produced
+        shutil.copy(os.path.join(opts["outputpath"], produced[0]), os.path.join(OUT, "dropin_" + produced[0]))
+        print("drop-in golden:", produced[0])
+
+
+if __name__ == "__main__" and "--dropin" in sys.argv:
+    make_dropin_goldens()
