@@ -195,7 +195,12 @@ def run_gpu(args, rank, world, local_rank):
         n = len(inp["points"])
         dout = (torch.empty((n, 6), dtype=torch.float32, device=dev) if kind == "field"
                 else torch.empty((n, 4), dtype=torch.float16, device=dev))
-    gathered = [torch.empty((1, 50, 50), dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
+    pending = []        # in-flight NCCL gathers of per-frame histograms (world > 1)
+
+    def drain():
+        for h, _, _ in pending:
+            h.wait()
+        pending.clear()
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     launches = {"n": 0}
     kern_ms = []
@@ -214,7 +219,12 @@ def run_gpu(args, rank, world, local_rank):
             eng.hist2d(dout, de, ce, out=dcounts)
             n_launch += work["k_launch"] + 1
             if world > 1:
-                dist.all_gather(gathered, dcounts)                       # the path's one exchange
+                # the path's one exchange: per-frame histograms to every rank.  Issued asynchronously
+                # on NCCL's stream from a snapshot of the counts, so the next frame's kernels never
+                # wait on communication; all handles are waited for before the timed region closes.
+                snap = dcounts.clone()
+                outs = [torch.empty_like(snap) for _ in range(world)]
+                pending.append((dist.all_gather(outs, snap, async_op=True), snap, outs))
         elif kind == "field":
             # device arm: the mesh is described by its axes (what the host entry point derives from the
             # flat list by itself, see cpet_field_grid); the e2e arm below hands over the flat list
@@ -248,16 +258,22 @@ def run_gpu(args, rank, world, local_rank):
         for _ in range(args.warmup):
             flush_buf.zero_()
             step_device()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        drain()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(args.steps + 1)]
         barrier()
         eng.kernel_times()               # reset the library's per-launch event record
         launches["n"] = 0
         sampler.start()
-        for a, b in evs:
+        for a, b in evs[:-1]:
             flush_buf.zero_()            # L2 flush, outside the per-step event bracket
             a.record()
+            drain()                      # previous frame's histogram gather (timed if it is late)
             step_device()
             b.record()
+        evs[-1][0].record()
+        drain()                          # the last frame's gather, inside its own timed bracket
+        evs[-1][1].record()
         barrier()
         sampler.stop()
         kern_ms[:] = eng.kernel_times()  # dominant kernel alone, one entry per timed step

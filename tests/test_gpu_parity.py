@@ -157,6 +157,18 @@ def test_field_edge_cases(M):
             assert relmax(M.field_grid(p, xm, qm, soften=True), f64.field_grid(p, xm, qm, True)) < FIELD_TOL
 
 
+def test_empty_charge_set(M):
+    """M = 0: fields and potentials are exactly zero; the unguarded E/|E| of the tracer gives NaN,
+    as the reference's 0/0 does (C:501)."""
+    x0 = np.zeros((0, 3), np.float32)
+    q0 = np.zeros(0, np.float32)
+    pts = synth.grid(3, 0.5)
+    assert np.all(M.field_grid(pts, x0, q0, soften=True) == 0.0)
+    assert np.all(M.esp_grid(pts, x0, q0) == 0.0)
+    out = M.topo_batch(pts[:5], np.full(5, 3), x0, q0, 0.1, np.array([0.5, 0.5, 0.5], np.float32))
+    assert np.all(np.isnan(out))
+
+
 def test_field_accumulation_at_100k_charges(M):
     """Heavy +/- cancellation (net-neutral 100k charges): FP32-in-tile / FP64-across-tiles holds
     1e-5 where a plain FP32 sequential sum (the reference) does not."""
