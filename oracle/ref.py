@@ -157,9 +157,15 @@ def _run_chunks(fn, n, threads):
     step = max(1, -(-n // (threads * 8)))
     spans = [(s, min(n, s + step)) for s in range(0, n, step)]
     _WORK = fn
+    import warnings
+
     try:
-        with mp.get_context("fork").Pool(threads) as pool:
-            done = sum(pool.imap_unordered(_call_work, spans))
+        with warnings.catch_warnings():
+            # the parent may hold OpenMP / CUDA helper threads; the children only run the reference's
+            # single-threaded C and never touch either, which is what the fork() warning is about
+            warnings.simplefilter("ignore", DeprecationWarning)
+            with mp.get_context("fork").Pool(threads) as pool:
+                done = sum(pool.imap_unordered(_call_work, spans))
         assert done == n
     finally:
         _WORK = None
