@@ -382,7 +382,8 @@ def run_gpu(args, rank, world, local_rank):
                      "algorithmic_bytes": int(work["units"]) * (28 if kind == "topo" else (36 if kind == "field" else 20))},
     }
     if world == 1:
-        line["cpu_baseline"] = cpu_baseline(kind, prm, inp, budget_s=args.cpu_seconds)
+        line["cpu_baseline"] = cpu_baseline(kind, prm, inp,
+                                            budget_s=12.0 if args.cpu_seconds is None else args.cpu_seconds)
     return line
 
 
@@ -448,6 +449,8 @@ def run_reference(args):
     kind, desc, prm = WORKLOADS[args.workload]
     inp = make_inputs(kind, prm, frame_id=0)
     budget = max(2.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    if args.cpu_seconds is not None:
+        budget = args.cpu_seconds
     cb = cpu_baseline(kind, prm, inp, budget_s=budget, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": "pair-evals/s", "value": cb["value"], "unit": "pair-evals/s",
@@ -468,7 +471,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="topo3a", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=None,
+                    help="CPU work per cpu_baseline sample (default 12 s; reference arm: sized from steps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
