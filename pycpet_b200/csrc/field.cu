@@ -17,6 +17,10 @@
 #include "cpet_internal.h"
 #include <cuda_fp16.h>
 
+#ifndef CPET_K1_UNROLL_P4
+#define CPET_K1_UNROLL_P4 2      // inner-loop unroll of the 4-points-per-thread general kernel
+#endif
+
 namespace cpet {
 
 // ---------------------------------------------------------------------------------------------
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(256) k1_grid_kernel(const K1Params prm) {
         const int stage = t % S;
         mbar_wait(&full[stage], (uint32_t)((t / S) & 1));
         const int n_t = min(TP, npairs - t * TP);
-        eval_tile_chunked<MODE, P, (P >= 4 ? 2 : 4), 64>(ring + (size_t)stage * TP, lane_g, n_t, G, r,
+        eval_tile_chunked<MODE, P, (P >= 4 ? CPET_K1_UNROLL_P4 : 4), 64>(ring + (size_t)stage * TP, lane_g, n_t, G, r,
                                                           acc);
         if (t + S < ntiles) {
             __syncthreads();           // every warp is done reading this stage
