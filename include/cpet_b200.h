@@ -41,7 +41,9 @@ extern "C" {
 #define CPET_ERR_STATE (-4)     /* call order: e.g. field requested before cpet_set_charges()     */
 
 int cpet_abi_version(void);
-/* Thread-local message / status of the most recent failing call on this thread ("" / 0 if none). */
+/* Thread-local message / status of the most recent failing call on this thread ("" / 0 if none).
+ * Sticky until cpet_clear_error(); every legacy `void` symbol clears it on entry, so after such a
+ * call the status is that call's own outcome. */
 const char *cpet_last_error(void);
 int cpet_last_status(void);
 void cpet_clear_error(void);
@@ -60,9 +62,13 @@ int cpet_sync(cpet_ctx *ctx);
 int cpet_device_of(cpet_ctx *ctx);
 /* Diagnostic: which K1 kernel served the last field/ESP call (0 general, 1 lattice). */
 int cpet_last_path(cpet_ctx *ctx);
-/* Tuning knobs for experiments: key in {"k1_threads","k1_points","k1_lanes","k1_tile_pairs",
- * "k1_stages","k2_threads","k2_lanes","k2_tile_pairs","k2_stages","k2_ctas_per_sm","k2_sort"};
- * value <= 0 restores the built-in heuristic. */
+/* Tuning knobs for experiments (the defaults are measured heuristics, profiles/round1_sweep.md):
+ * "k1_threads","k1_points" (points or z-nodes per thread),"k1_lanes" (lanes per point: 1, 8, 32),
+ * "k1_tile_pairs","k1_stages","k1_splits" (charge-range splits),"k1_unroll" (lattice kernel),
+ * "k1_lattice" (-1 auto-detect meshes in the host entry point, 0 off, 1 on),
+ * "k2_points" (lines per thread: 1, 2),"k2_threads","k2_lanes" (lanes per line: 1..32),
+ * "k2_tile_pairs","k2_stages","k2_sort" (-1 auto, 0, 1),"timing" (record kernel events).
+ * value <= 0 restores the built-in heuristic (except the three-state keys). */
 int cpet_set_tuning(cpet_ctx *ctx, const char *key, int value);
 /* Counters of the last kernel-launching call: [0]=kernels launched, [1]=pair evaluations
  * (algorithmic: points x charges, or sum over lines of (K+2) x charges), [2]=field evaluations. */

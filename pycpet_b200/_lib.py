@@ -115,8 +115,11 @@ def load() -> ctypes.CDLL:
 
 def check(status: int) -> None:
     if status != CPET_OK:
-        msg = load().cpet_last_error()
-        raise CpetError(f"libcpetb200 status {status}: {msg.decode() if msg else 'unknown error'}")
+        L = load()
+        msg = L.cpet_last_error()
+        text = msg.decode() if msg else "unknown error"
+        L.cpet_clear_error()
+        raise CpetError(f"libcpetb200 status {status}: {text}")
 
 
 def check_legacy() -> None:

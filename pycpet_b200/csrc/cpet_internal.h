@@ -45,7 +45,7 @@ struct Tuning {
     int k1_splits = 0;
     int k1_unroll = 0;     // lattice kernel inner-loop unroll (1, 2 or 4; 0 = default 2)
     int k1_lattice = -1;   // -1 auto (detect z-fastest tensor-product meshes in the host entry point), 0 off, 1 on
-    int k2_points = 0, k2_threads = 0, k2_lanes = 0, k2_tile_pairs = 0, k2_stages = 0, k2_ctas_per_sm = 0;
+    int k2_points = 0, k2_threads = 0, k2_lanes = 0, k2_tile_pairs = 0, k2_stages = 0;
     int k2_sort = -1;   // -1 heuristic (on), 0 off, 1 on
     int timing = 0;
 };
@@ -61,6 +61,7 @@ struct cpet_ctx {
     // current frame
     int n_charges = 0;
     int n_pairs = 0;                 // padded
+    bool charges_set = false;        // cpet_set_charges* has been called on this context
     cpet::DevBuf charges;            // ChargePair[n_pairs]
     cpet::DevBuf raw_x, raw_q;       // staging for host uploads
     // scratch

@@ -56,6 +56,7 @@ int launch_pack_charges(cpet_ctx* c, int n_charges, const float* d_x, const floa
     const int n_pairs = (n_charges + 1) / 2;
     if (int rc = c->charges.reserve(sizeof(ChargePair) * (size_t)(n_pairs > 0 ? n_pairs : 1))) return rc;
     c->n_charges = n_charges;
+    c->charges_set = true;
     c->n_pairs = n_pairs;
     if (n_pairs > 0) {
         pack_charges_kernel<<<(n_pairs + 255) / 256, 256, 0, c->stream>>>(
@@ -352,6 +353,7 @@ static int launch_k1_lat_inst(cpet_ctx* c, const K1LatParams& prm, dim3 grid, in
 int launch_field_lattice(cpet_ctx* c, int mode, int nx, int ny, int nz, const float* d_xs,
                          const float* d_ys, const float* d_zs, int out_kind, void* d_out) {
     const long long n_points_ll = (long long)nx * ny * nz;
+    CPET_REQUIRE(c->charges_set, CPET_ERR_STATE, "no charge set on this context: call cpet_set_charges first");
     c->last_counters[0] = 0;
     c->last_counters[1] = n_points_ll * (long long)c->n_charges;
     c->last_counters[2] = n_points_ll;
@@ -549,6 +551,7 @@ int detect_lattice(cpet_ctx* c, int n_points, const float* d_x0, int* is_lattice
 
 int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, int out_kind,
                       void* d_out, float step) {
+    CPET_REQUIRE(c->charges_set, CPET_ERR_STATE, "no charge set on this context: call cpet_set_charges first");
     c->last_counters[0] = 0;
     c->last_counters[1] = (int64_t)n_points * (int64_t)c->n_charges;
     c->last_counters[2] = n_points;

@@ -213,6 +213,7 @@ struct Stage {
 using namespace cpet;
 
 #define LEGACY_CTX_OR_FAIL(out, n)                          \
+    cpet_clear_error(); /* status = this call's outcome */  \
     std::lock_guard<std::mutex> lock(g_mu);                 \
     cpet_ctx* c = legacy_ctx();                             \
     if (!c) { fail_fill((out), (n)); return; }              \
@@ -318,6 +319,7 @@ void vecaddn(float* ret, float* A, float* B, int lenA) {
 }
 
 void dot(double* ret, double* A, double* B, int rows, int cols) {
+    cpet_clear_error();
     std::lock_guard<std::mutex> lock(g_mu);
     cpet_ctx* c = legacy_ctx();
     if (!c) { for (int i = 0; i < rows; ++i) ret[i] = NAN; return; }
@@ -331,6 +333,7 @@ void dot(double* ret, double* A, double* B, int rows, int cols) {
 void sparse_dot(double* ret, int* indptr, int indptrlen, int* indA, int lenindA, double* A, int lenA,
                 double* B, int size_array) {
     const int rows = indptrlen - 1;
+    cpet_clear_error();
     std::lock_guard<std::mutex> lock(g_mu);
     cpet_ctx* c = legacy_ctx();
     if (!c || rows <= 0) { for (int i = 0; i < rows; ++i) ret[i] = NAN; return; }

@@ -389,6 +389,7 @@ static int launch_k2_inst(cpet_ctx* c, const K2Params& prm, int grid, int thread
 
 int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d_n_iter,
                 float step, const float dims[3], unsigned flags, float* d_out, int32_t* d_steps) {
+    CPET_REQUIRE(c->charges_set, CPET_ERR_STATE, "no charge set on this context: call cpet_set_charges first");
     c->last_counters[0] = c->last_counters[1] = c->last_counters[2] = 0;
     if (n_lines == 0) return CPET_OK;
     const Tuning& tu = c->tune;

@@ -157,6 +157,32 @@ def test_field_edge_cases(M):
             assert relmax(M.field_grid(p, xm, qm, soften=True), f64.field_grid(p, xm, qm, True)) < FIELD_TOL
 
 
+def test_error_reporting():
+    """Negative status + message instead of garbage: call order, bad flags, bad sizes."""
+    from pycpet_b200 import CpetError, Math_ops, _lib
+
+    m = Math_ops()
+    pts = synth.grid(3, 0.5)
+    with pytest.raises(CpetError, match="cpet_set_charges"):
+        m.field_grid(pts)                                   # no charge set on this context yet
+    with pytest.raises(CpetError, match="cpet_set_charges"):
+        m.topo_batch(pts, np.ones(len(pts)), step_size=0.1, dimensions=(1, 1, 1))
+    x, Q = synth.charges(100, seed=0, box=0.5)
+    m.set_charges(x, Q)
+    out = np.zeros((len(pts), 3), np.float32)
+    rc = m.math.cpet_field_grid(m.ctx, len(pts), _lib.ptr(pts), 64, _lib.ptr(out))      # unknown flag bit
+    assert rc == -1 and b"flag" in m.math.cpet_last_error()
+    rc = m.math.cpet_field_grid(m.ctx, -5, _lib.ptr(pts), 0, _lib.ptr(out))
+    assert rc == -1
+    with pytest.raises(ValueError):
+        m.set_charges(x, Q[:-1])
+    with pytest.raises(CpetError, match="unknown tuning key"):
+        m.set_tuning(no_such_knob=1)
+    with pytest.raises(CpetError):
+        Math_ops(device=99).ctx
+    m.close()
+
+
 def test_empty_charge_set(M):
     """M = 0: fields and potentials are exactly zero; the unguarded E/|E| of the tracer gives NaN,
     as the reference's 0/0 does (C:501)."""
