@@ -25,6 +25,12 @@ struct __align__(16) PairB { u64 nz, q; };
 struct __align__(32) ChargePair { PairA a; PairB b; };
 static_assert(sizeof(ChargePair) == 32, "charge pair must be 32 bytes");
 
+// The same pairs in blocks of 32, structure-of-arrays inside a block (1 KB): lane l of a warp reads
+// a[l] and b[l] with two conflict-free LDS.128 (32 x 16 contiguous bytes each).  Used by the
+// warp-wide streamline kernel, where the 32 lanes of a warp split the charges of a frame.
+struct __align__(16) ChargeBlock { PairA a[32]; PairB b[32]; };
+static_assert(sizeof(ChargeBlock) == 1024, "charge block must be 1 KB");
+
 // A padding charge: q = 0 at a far but finite position (no inf*0 in the raw-field mode).
 #define CPET_PAD_COORD 1.0e8f
 

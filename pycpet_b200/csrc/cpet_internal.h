@@ -47,6 +47,8 @@ struct Tuning {
     int k1_lattice = -1;   // -1 auto (detect z-fastest tensor-product meshes in the host entry point), 0 off, 1 on
     int k2_points = 0, k2_threads = 0, k2_lanes = 0, k2_tile_pairs = 0, k2_stages = 0;
     int k2_sort = -1;   // -1 heuristic (on), 0 off, 1 on
+    int k2_impl = 0;    // 0 warp-wide kernel (default), 1 slot kernel (G lanes per line)
+    int k2_cap = 0;     // warp-wide kernel: streamlines per warp (1, 2, 4; 0 = heuristic)
     int timing = 0;
 };
 
@@ -63,6 +65,7 @@ struct cpet_ctx {
     int n_pairs = 0;                 // padded
     bool charges_set = false;        // cpet_set_charges* has been called on this context
     cpet::DevBuf charges;            // ChargePair[n_pairs]
+    cpet::DevBuf charge_blocks;      // ChargeBlock[ceil(n_pairs / 32)], zero-charge padded
     cpet::DevBuf raw_x, raw_q;       // staging for host uploads
     // scratch
     cpet::DevBuf in0, in1, out0, out1, work0, work1, work2, counters;

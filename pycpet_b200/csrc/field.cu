@@ -27,9 +27,10 @@ namespace cpet {
 // charge packing: (M,3) f32 + (M,) f32  ->  ChargePair[ceil(M/2)]
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_charges_kernel(const float* __restrict__ x, const float* __restrict__ q,
-                                    int n_charges, int n_pairs, ChargePair* __restrict__ out) {
+                                    int n_charges, int n_pairs, ChargePair* __restrict__ out,
+                                    ChargeBlock* __restrict__ blocks) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_pairs) return;
+    if (j >= ((n_pairs + 31) & ~31)) return;
     float cx[2], cy[2], cz[2], cq[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -49,7 +50,9 @@ __global__ void pack_charges_kernel(const float* __restrict__ x, const float* __
     cp.a.ny = pk2(cy[0], cy[1]);
     cp.b.nz = pk2(cz[0], cz[1]);
     cp.b.q = pk2(cq[0], cq[1]);
-    out[j] = cp;
+    if (j < n_pairs) out[j] = cp;
+    blocks[j >> 5].a[j & 31] = cp.a;      // the last block is padded with q = 0 pairs
+    blocks[j >> 5].b[j & 31] = cp.b;
 }
 
 int launch_pack_charges(cpet_ctx* c, int n_charges, const float* d_x, const float* d_q) {
@@ -58,9 +61,11 @@ int launch_pack_charges(cpet_ctx* c, int n_charges, const float* d_x, const floa
     c->n_charges = n_charges;
     c->charges_set = true;
     c->n_pairs = n_pairs;
+    const int n_blocks = (n_pairs + 31) / 32;
+    if (int rc = c->charge_blocks.reserve(sizeof(ChargeBlock) * (size_t)(n_blocks > 0 ? n_blocks : 1))) return rc;
     if (n_pairs > 0) {
-        pack_charges_kernel<<<(n_pairs + 255) / 256, 256, 0, c->stream>>>(
-            d_x, d_q, n_charges, n_pairs, c->charges.as<ChargePair>());
+        pack_charges_kernel<<<(n_blocks * 32 + 255) / 256, 256, 0, c->stream>>>(
+            d_x, d_q, n_charges, n_pairs, c->charges.as<ChargePair>(), c->charge_blocks.as<ChargeBlock>());
         CPET_CUDA_TRY(cudaGetLastError());
     }
     return CPET_OK;

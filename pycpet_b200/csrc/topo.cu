@@ -315,6 +315,364 @@ __global__ void __launch_bounds__(CPET_K2_MAXT, 1) k2_topo_kernel(const K2Params
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2W: warp-wide integrator.  A warp owns up to 4 streamlines at a time; its 32 lanes split the
+// charges of the frame (lane l evaluates pairs l, l+32, ... of the blocked charge layout) and
+// every lane evaluates all of the warp's current points against each pair it loads -- the
+// 4-points-per-thread register blocking of K1, so one pair of LDS.128 feeds 8 pair-evaluations.
+// After the pass the 12 FP64 sums are butterfly-reduced over the warp and lane q (mirrored by
+// lanes q+4, q+8, ...) advances the state machine of line q.  Compared with the slot kernel above:
+//   * lane utilisation does not depend on how many lines the warp holds (PE = 4, 2 or 1 points
+//     are evaluated per pass, compacted), so the end of the queue costs ~one short pass, not
+//     32/G idle lanes for the length of a line;
+//   * no lanes-per-line heuristic, and shared-memory traffic per pair-evaluation is that of G = 1
+//     for any number of lines (the slot kernel needs G >= 4 for short queues and then saturates
+//     the shared-memory pipe with G distinct addresses per LDS).
+// ---------------------------------------------------------------------------------------------
+struct K2WParams {
+    const ChargeBlock* blocks;
+    int n_blocks;
+    int tile_blocks;
+    int stages;
+    int ntiles;
+    int resident;
+    int cap;                // streamlines per warp (1, 2 or 4)
+    const float* seeds;
+    const int32_t* n_iter;
+    const int32_t* order;
+    int n_lines;
+    float h;
+    float dimx, dimy, dimz;
+    float* out;
+    int32_t* steps;
+    unsigned int* queue;
+    unsigned long long* evals;
+};
+
+template <int PE>
+__device__ __forceinline__ void evalw_pair(const PairA a, const PairB b, PointRegs<4>& r) {
+#pragma unroll
+    for (int p = 0; p < PE; ++p) {
+        const u64 dx = add2(r.px[p], a.nx);
+        const u64 dy = add2(r.py[p], a.ny);
+        const u64 dz = add2(r.pz[p], b.nz);
+        u64 r2 = mul2(dx, dx);
+        r2 = fma2(dy, dy, r2);
+        r2 = fma2(dz, dz, r2);
+        float r2a, r2b;
+        upk2(r2, r2a, r2b);
+        const u64 inv = pk2(rsqrt_approx(r2a), rsqrt_approx(r2b));
+        const u64 t = mul2(inv, inv);
+        const u64 u = mul2(inv, b.q);
+        const u64 s = mul2(t, u);
+        r.ax[p] = fma2(s, dx, r.ax[p]);
+        r.ay[p] = fma2(s, dy, r.ay[p]);
+        r.az[p] = fma2(s, dz, r.az[p]);
+    }
+}
+
+// blocks [0, nblk): lane `lane` takes pair `lane` of every block; FP32 partials are folded into
+// the FP64 sums every CPET_K2W_CHUNK blocks (one FP32 chain is at most that many additions).
+#ifndef CPET_K2W_CHUNK
+#define CPET_K2W_CHUNK 128
+#endif
+template <int PE, int U>
+__device__ __forceinline__ void evalw_range(const ChargeBlock* __restrict__ blk, int nblk, int lane,
+                                            PointRegs<4>& r, double (&acc)[4][3]) {
+    for (int b0 = 0; b0 < nblk; b0 += CPET_K2W_CHUNK) {
+        const int b1 = min(nblk, b0 + CPET_K2W_CHUNK);
+#pragma unroll U
+        for (int b = b0; b < b1; ++b) {
+            const PairA a = blk[b].a[lane];
+            const PairB bb = blk[b].b[lane];
+            evalw_pair<PE>(a, bb, r);
+        }
+#pragma unroll
+        for (int p = 0; p < PE; ++p) {
+            float lo, hi;
+            upk2(r.ax[p], lo, hi);
+            acc[p][0] += (double)(lo + hi);
+            upk2(r.ay[p], lo, hi);
+            acc[p][1] += (double)(lo + hi);
+            upk2(r.az[p], lo, hi);
+            acc[p][2] += (double)(lo + hi);
+            r.ax[p] = r.ay[p] = r.az[p] = 0ull;
+        }
+    }
+}
+
+// One halving step of a transposing warp reduction: lanes whose `upper` flag is clear keep `a` and
+// hand `b` to their partner (lane ^ m); the others keep `b` and hand over `a`.
+__device__ __forceinline__ double xchg_add(double a, double b, int m, bool upper) {
+    const double keep = upper ? b : a;
+    const double send = upper ? a : b;
+    return keep + shfl_xor_f64(send, m);
+}
+
+// Sum acc[p][0..2] (p < PE) over the 32 lanes.  On return (ex,ey,ez) in lane l holds the total of
+// position l / (32/PE), i.e. PE = 4: lanes 8p..8p+7 hold position p.  90 / 57 / 45 instructions
+// for PE = 4 / 2 / 1 instead of 45 per position for a plain butterfly.
+template <int PE>
+__device__ __forceinline__ void reduce_positions(const double (&acc)[4][3], int lane, double& ex,
+                                                 double& ey, double& ez) {
+    double v[3];
+    if (PE == 4) {
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+        double w[2][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            w[0][c] = xchg_add(acc[0][c], acc[2][c], 16, up16);   // low half: positions 0,1; high: 2,3
+            w[1][c] = xchg_add(acc[1][c], acc[3][c], 16, up16);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = xchg_add(w[0][c], w[1][c], 8, up8);
+#pragma unroll
+        for (int m = 4; m >= 1; m >>= 1)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] += shfl_xor_f64(v[c], m);
+    } else if (PE == 2) {
+        const bool up16 = (lane & 16) != 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = xchg_add(acc[0][c], acc[1][c], 16, up16);
+#pragma unroll
+        for (int m = 8; m >= 1; m >>= 1)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] += shfl_xor_f64(v[c], m);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = acc[0][c];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] += shfl_xor_f64(v[c], m);
+    }
+    ex = v[0]; ey = v[1]; ez = v[2];
+}
+
+// State of the (up to) 4 streamlines of one warp, in shared memory so that none of it occupies
+// registers during the charge loop.  Arrays of 4 = one entry per line slot.
+struct __align__(16) WarpLines {
+    float px[4], py[4], pz[4];         // current point p_k
+    float sx[4], sy[4], sz[4];         // seed
+    double ux[4], uy[4], uz[4];        // unit field direction at p_{k-1}
+    double ex[4], ey[4], ez[4];        // field sums of the current pass
+    float dist[4], kinit[4];
+    int line[4], n_it[4], k[4], k_end[4];
+    float m1x[4], m1y[4], m1z[4], m2x[4], m2y[4], m2z[4];   // p_{k-1}, p_{k-2} (second-difference mode)
+};
+
+template <bool SD, int U4, int U2>
+__global__ void __launch_bounds__(CPET_K2_MAXT, 1) k2w_topo_kernel(const K2WParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    WarpLines* lines_all = reinterpret_cast<WarpLines*>(smem_raw + 128);
+    const int n_warps = blockDim.x >> 5;
+    ChargeBlock* ring = reinterpret_cast<ChargeBlock*>(smem_raw + 128 + sizeof(WarpLines) * n_warps);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    WarpLines& W = lines_all[tid >> 5];
+    const bool owner = lane < 4;       // lane q < 4 runs the state machine of line slot q
+    const int S = prm.stages;
+    const int TB = prm.tile_blocks;
+    const int NT = prm.ntiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (owner) W.line[lane] = -1;
+    __syncthreads();
+
+    auto issue = [&](int it) {
+        const int stage = it % S;
+        const int t = it % NT;
+        const int n_t = min(TB, prm.n_blocks - t * TB);
+        const uint32_t bytes = (uint32_t)n_t * (uint32_t)sizeof(ChargeBlock);
+        mbar_expect_tx(&full[stage], bytes);
+        tma_load_1d(ring + (size_t)stage * TB, prm.blocks + (size_t)t * TB, bytes, &full[stage]);
+    };
+    int issued = 0;
+    if (tid == 0) {
+        const int pre = prm.resident ? NT : min(S, NT);
+        for (; issued < pre; ++issued) issue(issued);
+    }
+    if (prm.resident) {
+        for (int t = 0; t < NT; ++t) mbar_wait(&full[t], 0u);
+    }
+
+    bool exhausted = false;
+    unsigned long long my_evals = 0ull;
+    const double h = (double)prm.h;
+    const double inv_h = 1.0 / h;
+
+    int it = 0;   // consumed-tile counter (streamed mode)
+    while (true) {
+        // ---- refill the warp's empty line slots from the queue (one atomic per warp) ------------
+        {
+            const bool empty = owner && W.line[lane] < 0;
+            const unsigned em = __ballot_sync(0xffffffffu, empty);
+            const int n_empty = __popc(em);
+            int want = min(n_empty, prm.cap - (4 - n_empty));
+            if (exhausted) want = 0;
+            if (want > 0) {                                    // warp-uniform
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(prm.queue, (unsigned)want);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int rank = __popc(em & ((1u << lane) - 1u));
+                const unsigned slot = base + (unsigned)rank;
+                if (empty && rank < want && slot < (unsigned)prm.n_lines) {
+                    const int line = prm.order ? prm.order[slot] : (int)slot;
+                    const float sx = prm.seeds[3 * (size_t)line];
+                    const float sy = prm.seeds[3 * (size_t)line + 1];
+                    const float sz = prm.seeds[3 * (size_t)line + 2];
+                    const int n_it = prm.n_iter[line];
+                    W.line[lane] = line;
+                    W.sx[lane] = sx; W.sy[lane] = sy; W.sz[lane] = sz;
+                    W.px[lane] = sx; W.py[lane] = sy; W.pz[lane] = sz;
+                    if (SD) {
+                        W.m1x[lane] = W.m2x[lane] = sx; W.m1y[lane] = W.m2y[lane] = sy;
+                        W.m1z[lane] = W.m2z[lane] = sz;
+                    }
+                    W.n_it[lane] = n_it;
+                    W.k[lane] = 0;
+                    W.k_end[lane] = (n_it <= 0) ? 0 : -1;
+                    W.dist[lane] = 0.f;
+                    W.kinit[lane] = 0.f;
+                    W.ux[lane] = W.uy[lane] = W.uz[lane] = 0.0;
+                }
+                if (base + (unsigned)want >= (unsigned)prm.n_lines) exhausted = true;
+            }
+        }
+        const unsigned am = __ballot_sync(0xffffffffu, owner && W.line[lane] >= 0);   // also orders the stores above
+        bool go;
+        if (prm.resident) go = (am != 0u);
+        else go = __syncthreads_or(am != 0u ? 1 : 0) != 0;
+        if (!go) break;
+
+        // ---- the warp's current points, compacted to positions 0..na-1 ----------------------------
+        const int na = __popc(am);
+        int src[4];
+        PointRegs<4> r;
+        double acc[4][3];
+        {
+            unsigned m = am;
+            const int first = am ? (__ffs(am) - 1) : 0;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                src[p] = m ? (__ffs(m) - 1) : first;           // unused positions repeat a valid point
+                m &= m - 1u;
+                set_point<4>(r, p, W.px[src[p]], W.py[src[p]], W.pz[src[p]]);
+                acc[p][0] = acc[p][1] = acc[p][2] = 0.0;
+            }
+            clear_partials<4>(r);
+        }
+
+        // ---- field at those points: all charges, split over the 32 lanes -----------------------------
+        if (prm.resident) {
+            if (na > 2) evalw_range<4, U4>(ring, prm.n_blocks, lane, r, acc);
+            else if (na == 2) evalw_range<2, U2>(ring, prm.n_blocks, lane, r, acc);
+            else evalw_range<1, 8>(ring, prm.n_blocks, lane, r, acc);
+        } else {
+            for (int t = 0; t < NT; ++t, ++it) {
+                const int stage = it % S;
+                mbar_wait(&full[stage], (uint32_t)((it / S) & 1));
+                const int n_t = min(TB, prm.n_blocks - t * TB);
+                const ChargeBlock* tile = ring + (size_t)stage * TB;
+                if (na > 2) evalw_range<4, U4>(tile, n_t, lane, r, acc);
+                else if (na == 2) evalw_range<2, U2>(tile, n_t, lane, r, acc);
+                else if (na == 1) evalw_range<1, 8>(tile, n_t, lane, r, acc);
+                __syncthreads();                      // stage fully consumed by the CTA
+                if (tid == 0) { issue(issued); ++issued; }   // speculative: next pass's tiles too
+            }
+        }
+
+        // ---- warp reduction of the FP64 sums; the total of position p goes to line slot src[p] ---
+        {
+            double ex, ey, ez;
+            int pos;                                           // position whose total this lane holds
+            if (na > 2) { reduce_positions<4>(acc, lane, ex, ey, ez); pos = lane >> 3; }
+            else if (na == 2) { reduce_positions<2>(acc, lane, ex, ey, ez); pos = lane >> 4; }
+            else { reduce_positions<1>(acc, lane, ex, ey, ez); pos = 0; }
+            const int slot = pos == 0 ? src[0] : (pos == 1 ? src[1] : (pos == 2 ? src[2] : src[3]));
+            if ((lane & 7) == 0 && pos < na && (na > 2 || (lane & 15) == 0) && (na > 1 || lane == 0)) {
+                W.ex[slot] = ex; W.ey[slot] = ey; W.ez[slot] = ez;
+            }
+        }
+        __syncwarp();
+
+        // ---- state machine of line slot `lane` ----------------------------------------------------------
+        if (owner && ((am >> lane) & 1u)) {
+            const int q = lane;
+            const double ex = W.ex[q], ey = W.ey[q], ez = W.ez[q];
+            const float px = W.px[q], py = W.py[q], pz = W.pz[q];
+            int k = W.k[q];
+            const int k_end = W.k_end[q];
+            // unit direction (no zero guard: E = 0 gives NaN exactly like C:501)
+            const double inv_n = rsqrt_f64_fast(ex * ex + ey * ey + ez * ez);
+            const double ux = ex * inv_n, uy = ey * inv_n, uz = ez * inv_n;
+            const bool last = (k_end >= 0) && (k == k_end + 1);
+            float kdir = 0.f;
+            if (!SD && (k == 1 || last)) {   // curvature is needed at the first and last point pair
+                const double pux = W.ux[q], puy = W.uy[q], puz = W.uz[q];
+                const double cx = puy * uz - puz * uy;
+                const double cy = puz * ux - pux * uz;
+                const double cz = pux * uy - puy * ux;
+                kdir = (float)(sqrt_f64_fast(cx * cx + cy * cy + cz * cz) * inv_h);
+                if (k == 1) W.kinit[q] = kdir;
+            }
+            const float nx = (float)((double)px + h * ux);
+            const float ny = (float)((double)py + h * uy);
+            const float nz = (float)((double)pz + h * uz);
+            if (last) {
+                if (SD) {
+                    kdir = curv3_f32(make_float3(W.m1x[q], W.m1y[q], W.m1z[q]), make_float3(px, py, pz),
+                                     make_float3(nx, ny, nz));
+                    if (k == 1) W.kinit[q] = kdir;
+                }
+                const int line = W.line[q];
+                reinterpret_cast<float2*>(prm.out)[line] = make_float2(W.dist[q], (W.kinit[q] + kdir) * 0.5f);
+                if (prm.steps) prm.steps[line] = k_end;
+                my_evals += (unsigned long long)(k_end + 2);
+                W.line[q] = -1;
+            } else {
+                if (SD) {
+                    W.m2x[q] = W.m1x[q]; W.m2y[q] = W.m1y[q]; W.m2z[q] = W.m1z[q];
+                    W.m1x[q] = px; W.m1y[q] = py; W.m1z[q] = pz;
+                }
+                W.px[q] = nx; W.py[q] = ny; W.pz[q] = nz;
+                ++k;
+                W.k[q] = k;
+                if (SD && k == 2)
+                    W.kinit[q] = curv3_f32(make_float3(W.m2x[q], W.m2y[q], W.m2z[q]),
+                                           make_float3(W.m1x[q], W.m1y[q], W.m1z[q]), make_float3(nx, ny, nz));
+                if (k_end < 0) {
+                    const bool outside = (nx < -prm.dimx) || (nx > prm.dimx) || (ny < -prm.dimy) ||
+                                         (ny > prm.dimy) || (nz < -prm.dimz) || (nz > prm.dimz);
+                    if (k >= W.n_it[q] || outside) {
+                        W.k_end[q] = k;
+                        const double ddx = (double)W.sx[q] - (double)nx;
+                        const double ddy = (double)W.sy[q] - (double)ny;
+                        const double ddz = (double)W.sz[q] - (double)nz;
+                        W.dist[q] = (float)sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+                    }
+                }
+                W.ux[q] = ux; W.uy[q] = uy; W.uz[q] = uz;
+            }
+        }
+        __syncwarp();
+    }
+
+    if (!prm.resident) {
+        // drain the speculative loads before the CTA (and its shared memory) retires
+        if (tid == 0) {
+            for (; it < issued; ++it) mbar_wait(&full[it % S], (uint32_t)((it / S) & 1));
+        }
+    }
+    if (my_evals) atomicAdd(prm.evals, my_evals);
+}
+
+// ---------------------------------------------------------------------------------------------
 // queue ordering: counting sort of line ids by n_iter, descending (LPT), block-aggregated.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int k2_key(int n_iter) {
@@ -387,11 +745,38 @@ static int launch_k2_inst(cpet_ctx* c, const K2Params& prm, int grid, int thread
     return CPET_OK;
 }
 
-int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d_n_iter,
+// queue order (LPT): line ids sorted by n_iter descending into c->work1; leaves `order` null when
+// the sort is skipped.  Also zeroes the queue cursor / evaluation counter block.
+static int prepare_queue(cpet_ctx* c, int n_lines, const int32_t* d_n_iter, bool do_sort,
+                         unsigned int** queue, unsigned long long** evals, const int32_t** order,
+                         int* launches) {
+    const int sms = c->sm_count;
+    if (int rc = c->counters.reserve(64 + sizeof(unsigned) * 3 * K2_KEYMAX)) return rc;
+    unsigned char* cb = c->counters.as<unsigned char>();
+    CPET_CUDA_TRY(cudaMemsetAsync(cb, 0, 64 + sizeof(unsigned) * 3 * K2_KEYMAX, c->stream));
+    *queue = reinterpret_cast<unsigned int*>(cb);
+    *evals = reinterpret_cast<unsigned long long*>(cb + 8);
+    unsigned* hist = reinterpret_cast<unsigned*>(cb + 64);
+    unsigned* offsets = hist + K2_KEYMAX;
+    unsigned* cursor = offsets + K2_KEYMAX;
+    *order = nullptr;
+    if (do_sort) {
+        if (int rc = c->work1.reserve(sizeof(int32_t) * (size_t)n_lines)) return rc;
+        int blocks = (n_lines + 255) / 256;
+        if (blocks > sms * 8) blocks = sms * 8;
+        k2_count_kernel<<<blocks, 256, 0, c->stream>>>(d_n_iter, n_lines, hist);
+        k2_scan_kernel<<<1, 1024, 0, c->stream>>>(hist, offsets);
+        k2_scatter_kernel<<<blocks, 256, 0, c->stream>>>(d_n_iter, n_lines, offsets, cursor,
+                                                         c->work1.as<int32_t>());
+        CPET_CUDA_TRY(cudaGetLastError());
+        *order = c->work1.as<int32_t>();
+        *launches += 3;
+    }
+    return CPET_OK;
+}
+
+static int launch_topo_slots(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d_n_iter,
                 float step, const float dims[3], unsigned flags, float* d_out, int32_t* d_steps) {
-    CPET_REQUIRE(c->charges_set, CPET_ERR_STATE, "no charge set on this context: call cpet_set_charges first");
-    c->last_counters[0] = c->last_counters[1] = c->last_counters[2] = 0;
-    if (n_lines == 0) return CPET_OK;
     const Tuning& tu = c->tune;
     const int sms = c->sm_count;
     int launches = 0;
@@ -455,28 +840,8 @@ int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d
 
     // --- queue order ---------------------------------------------------------------------------
     const bool do_sort = (tu.k2_sort < 0) ? (n_lines > (int)slots_per_cta * grid) : (tu.k2_sort != 0);
-    if (int rc = c->counters.reserve(64 + sizeof(unsigned) * 3 * K2_KEYMAX)) return rc;
-    unsigned char* cb = c->counters.as<unsigned char>();
-    CPET_CUDA_TRY(cudaMemsetAsync(cb, 0, 64 + sizeof(unsigned) * 3 * K2_KEYMAX, c->stream));
-    prm.queue = reinterpret_cast<unsigned int*>(cb);
-    prm.evals = reinterpret_cast<unsigned long long*>(cb + 8);
-    unsigned* hist = reinterpret_cast<unsigned*>(cb + 64);
-    unsigned* offsets = hist + K2_KEYMAX;
-    unsigned* cursor = offsets + K2_KEYMAX;
-    prm.order = nullptr;
-
-    if (do_sort) {
-        if (int rc = c->work1.reserve(sizeof(int32_t) * (size_t)n_lines)) return rc;
-        int blocks = (n_lines + 255) / 256;
-        if (blocks > sms * 8) blocks = sms * 8;
-        k2_count_kernel<<<blocks, 256, 0, c->stream>>>(d_n_iter, n_lines, hist);
-        k2_scan_kernel<<<1, 1024, 0, c->stream>>>(hist, offsets);
-        k2_scatter_kernel<<<blocks, 256, 0, c->stream>>>(d_n_iter, n_lines, offsets, cursor,
-                                                         c->work1.as<int32_t>());
-        CPET_CUDA_TRY(cudaGetLastError());
-        prm.order = c->work1.as<int32_t>();
-        launches += 3;
-    }
+    if (int rc = prepare_queue(c, n_lines, d_n_iter, do_sort, &prm.queue, &prm.evals, &prm.order, &launches))
+        return rc;
 
     prm.seeds = d_seeds;
     prm.n_iter = d_n_iter;
@@ -509,6 +874,111 @@ int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d
     c->last_counters[1] = -1;   // resolved lazily from the device counter (see capi.cu)
     c->last_counters[2] = -1;
     return CPET_OK;
+}
+
+template <bool SD, int U4, int U2>
+static int launch_k2w_inst(cpet_ctx* c, const K2WParams& prm, int grid, int threads, size_t smem) {
+    auto kern = k2w_topo_kernel<SD, U4, U2>;
+    CPET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, c->stream>>>(prm);
+    CPET_CUDA_TRY(cudaGetLastError());
+    return CPET_OK;
+}
+
+static int launch_topo_warpwide(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d_n_iter,
+                                float step, const float dims[3], unsigned flags, float* d_out,
+                                int32_t* d_steps) {
+    const Tuning& tu = c->tune;
+    const int sms = c->sm_count;
+    int launches = 0;
+
+    // --- warps per CTA ---------------------------------------------------------------------------------
+    int threads = tu.k2_threads > 0 ? tu.k2_threads : 512;
+    threads = (threads / 32) * 32;
+    if (threads < 32) threads = 32;
+    if (threads > CPET_K2_MAXT) threads = CPET_K2_MAXT;
+    const int warps_per_cta = threads / 32;
+    const size_t hdr = 128 + sizeof(WarpLines) * (size_t)warps_per_cta;   // barriers + per-warp line state
+
+    // --- charge staging plan: whole frame resident in shared memory when it fits ------------------
+    const int n_blocks = (c->n_pairs + 31) / 32;
+    const size_t all_bytes = (size_t)n_blocks * sizeof(ChargeBlock);
+    K2WParams prm;
+    prm.blocks = c->charge_blocks.as<ChargeBlock>();
+    prm.n_blocks = n_blocks;
+    size_t smem;
+    if (hdr + all_bytes <= (size_t)c->max_smem_optin && tu.k2_stages <= 0 && tu.k2_tile_pairs <= 0) {
+        prm.resident = 1;
+        prm.tile_blocks = 32;                        // 32 KB per bulk copy
+        prm.ntiles = (n_blocks + prm.tile_blocks - 1) / prm.tile_blocks;
+        if (prm.ntiles > 15) {                       // at most 16 mbarriers in the 128-byte header
+            prm.tile_blocks = (n_blocks + 14) / 15;
+            prm.ntiles = (n_blocks + prm.tile_blocks - 1) / prm.tile_blocks;
+        }
+        prm.stages = prm.ntiles > 0 ? prm.ntiles : 1;
+        smem = hdr + all_bytes;
+    } else {
+        prm.resident = 0;
+        prm.tile_blocks = (tu.k2_tile_pairs > 0 ? tu.k2_tile_pairs : 2048) / 32;
+        if (prm.tile_blocks < 1) prm.tile_blocks = 1;
+        prm.stages = tu.k2_stages > 0 ? tu.k2_stages : 3;
+        if (prm.stages > 8) prm.stages = 8;
+        if (prm.stages < 2) prm.stages = 2;
+        while (prm.tile_blocks > 1 &&
+               hdr + (size_t)prm.stages * prm.tile_blocks * sizeof(ChargeBlock) > (size_t)c->max_smem_optin)
+            prm.tile_blocks /= 2;
+        prm.ntiles = (n_blocks + prm.tile_blocks - 1) / prm.tile_blocks;
+        smem = hdr + (size_t)prm.stages * prm.tile_blocks * sizeof(ChargeBlock);
+    }
+
+    // --- lines per warp ----------------------------------------------------------------------------
+    const long long all_warps = (long long)sms * warps_per_cta;
+    int cap = tu.k2_cap;
+    if (cap != 1 && cap != 2 && cap != 4) {
+        // 4 lines per warp once every warp of the chip gets that many in the first wave; fewer for
+        // short queues, so that the lines spread over all SMs instead of filling the first warps.
+        cap = n_lines >= 4 * all_warps ? 4 : (n_lines >= 2 * all_warps ? 2 : 1);
+    }
+    prm.cap = cap;
+    int grid = sms;
+    const long long need_ctas = (n_lines + (long long)warps_per_cta * cap - 1) / ((long long)warps_per_cta * cap);
+    if (need_ctas < grid) grid = (int)need_ctas;
+
+    const long long slots = (long long)grid * warps_per_cta * cap;
+    const bool do_sort = (tu.k2_sort < 0) ? (n_lines > slots) : (tu.k2_sort != 0);
+    if (int rc = prepare_queue(c, n_lines, d_n_iter, do_sort, &prm.queue, &prm.evals, &prm.order, &launches))
+        return rc;
+
+    prm.seeds = d_seeds;
+    prm.n_iter = d_n_iter;
+    prm.n_lines = n_lines;
+    prm.h = step;
+    prm.dimx = dims[0]; prm.dimy = dims[1]; prm.dimz = dims[2];
+    prm.out = d_out;
+    prm.steps = d_steps;
+
+    KernelTimer timer(c);   // brackets the integrator kernel only (the roofline's "dominant kernel")
+    const bool sd = (flags & CPET_TOPO_CURV_SECOND_DIFF) != 0u;
+    // inner-loop unroll: 4 blocks x 4 points (192 packed FMA-pipe instructions per iteration, no
+    // register-rotation MOVs at the back edge; U = 2 leaves 24 MOVs per 96 -- profiles/round1_k2w.md)
+    const int rc = sd ? launch_k2w_inst<true, 4, 4>(c, prm, grid, threads, smem)
+                      : launch_k2w_inst<false, 4, 4>(c, prm, grid, threads, smem);
+    if (rc) return rc;
+    launches += 1;
+    c->last_counters[0] = launches;
+    c->last_counters[1] = -1;   // resolved lazily from the device counter (see capi.cu)
+    c->last_counters[2] = -1;
+    return CPET_OK;
+}
+
+int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d_n_iter,
+                float step, const float dims[3], unsigned flags, float* d_out, int32_t* d_steps) {
+    CPET_REQUIRE(c->charges_set, CPET_ERR_STATE, "no charge set on this context: call cpet_set_charges first");
+    c->last_counters[0] = c->last_counters[1] = c->last_counters[2] = 0;
+    if (n_lines == 0) return CPET_OK;
+    if (c->tune.k2_impl == 1)
+        return launch_topo_slots(c, n_lines, d_seeds, d_n_iter, step, dims, flags, d_out, d_steps);
+    return launch_topo_warpwide(c, n_lines, d_seeds, d_n_iter, step, dims, flags, d_out, d_steps);
 }
 
 }  // namespace cpet

@@ -1,0 +1,14 @@
+import os, sys, numpy as np, torch
+ROOT = "/root/repo"
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import synth
+from pycpet_b200.device import Engine
+eng = Engine(0)
+x, Q = synth.charges(7890, seed=1, box=0.5)
+eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
+seeds, n_iter, dims, _ = synth.seeds(47, 0.5, 0.1)
+sd = torch.from_numpy(seeds).cuda(); ni = torch.from_numpy(n_iter.astype(np.int32)).cuda()
+for cfg in [dict(k2_cap=4), dict(k2_cap=2), dict(k2_impl=1)]:
+    eng.set_tuning(k2_cap=0, k2_impl=0); eng.set_tuning(**cfg)
+    eng.topo_batch(sd, ni, 0.1, dims)
+torch.cuda.synchronize(); print("done")
