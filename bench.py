@@ -42,9 +42,9 @@ ESP_FLOPS_PER_PAIR = 11.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.5: 148 SM x 128 lanes x 2 x 1.965 GHz
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
-# `ncu --set full` capture summarised in profiles/round1_ncu_summary.md (same inputs as the bench)
+# `ncu --set full` capture summarised in profiles/round1_k2w_ncu.md (same inputs as the bench)
 NCU_TRAFFIC = {
-    "topo3a": (2236416, "profiles/round1_ncu_summary.md k2_topo_kernel<2,1,0>: 2.24 MB read + 0 B written back "
+    "topo3a": (2265344, "profiles/round1_k2w_ncu.md k2w_topo_kernel<0,4,4>: 2.27 MB read + 0 B written back "
                         "during the kernel (seeds 12 B + n_iter 4 B + queue order 4 B per line; the 8 B/line "
                         "output is still in L2 when the kernel ends)"),
 }
@@ -370,7 +370,7 @@ def run_gpu(args, rank, world, local_rank):
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": t_e2e / args.steps * 1e3},
         "gpu_launches": int(launches["n"]),
-        "roofline": {"bound": "fp32-non-tensor", "kernel": "k2_topo_kernel" if kind == "topo" else "k1_grid_kernel",
+        "roofline": {"bound": "fp32-non-tensor", "kernel": "k2w_topo_kernel" if kind == "topo" else "k1_grid_kernel",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_source": "measured live: register-resident FMA loop (cpet_fp32_peak_probe, "
                                     f"FFMA2 {peak_ffma2:.1f} / FFMA {peak_ffma:.1f} TFLOP/s); "

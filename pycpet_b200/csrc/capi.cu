@@ -163,7 +163,7 @@ int cpet_destroy(cpet_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->charges.release(); c->charge_blocks.release(); c->raw_x.release(); c->raw_q.release();
     c->in0.release(); c->in1.release(); c->out0.release(); c->out1.release();
-    c->work0.release(); c->work1.release(); c->work2.release(); c->counters.release();
+    c->work0.release(); c->work1.release(); c->work2.release(); c->counters.release(); c->flags.release();
     for (int i = 0; i < cpet_ctx::kTimerRing; ++i) {
         if (c->ev0[i]) cudaEventDestroy(c->ev0[i]);
         if (c->ev1[i]) cudaEventDestroy(c->ev1[i]);
@@ -187,14 +187,14 @@ int cpet_set_tuning(cpet_ctx* c, const char* key, int value) {
     Tuning& t = c->tune;
     struct { const char* k; int* v; } tab[] = {
         {"k1_threads", &t.k1_threads}, {"k1_points", &t.k1_points}, {"k1_lanes", &t.k1_lanes},
-        {"k1_tile_pairs", &t.k1_tile_pairs}, {"k1_stages", &t.k1_stages}, {"k1_splits", &t.k1_splits}, {"k1_lattice", &t.k1_lattice}, {"k1_unroll", &t.k1_unroll},
+        {"k1_tile_pairs", &t.k1_tile_pairs}, {"k1_stages", &t.k1_stages}, {"k1_splits", &t.k1_splits}, {"k1_lattice", &t.k1_lattice}, {"k1_unroll", &t.k1_unroll}, {"k1_softscan", &t.k1_softscan},
         {"k2_points", &t.k2_points}, {"k2_threads", &t.k2_threads}, {"k2_lanes", &t.k2_lanes}, {"k2_tile_pairs", &t.k2_tile_pairs},
         {"k2_stages", &t.k2_stages}, {"k2_sort", &t.k2_sort}, {"k2_impl", &t.k2_impl}, {"k2_cap", &t.k2_cap},
         {"timing", &t.timing},
     };
     for (auto& e : tab) {
         if (strcmp(e.k, key) == 0) {
-            if (e.v == &t.k2_sort || e.v == &t.k1_lattice) *e.v = value;
+            if (e.v == &t.k2_sort || e.v == &t.k1_lattice || e.v == &t.k1_softscan) *e.v = value;
             else *e.v = value > 0 ? value : 0;
             return CPET_OK;
         }

@@ -45,6 +45,7 @@ struct Tuning {
     int k1_splits = 0;
     int k1_unroll = 0;     // lattice kernel inner-loop unroll (1, 2 or 4; 0 = default 2)
     int k1_lattice = -1;   // -1 auto (detect z-fastest tensor-product meshes in the host entry point), 0 off, 1 on
+    int k1_softscan = -1;  // lattice kernel: -1 auto (scan for charges on grid nodes when the mesh is large), 0 off, 1 on
     int k2_points = 0, k2_threads = 0, k2_lanes = 0, k2_tile_pairs = 0, k2_stages = 0;
     int k2_sort = -1;   // -1 heuristic (on), 0 off, 1 on
     int k2_impl = 0;    // 0 warp-wide kernel (default), 1 slot kernel (G lanes per line)
@@ -68,7 +69,7 @@ struct cpet_ctx {
     cpet::DevBuf charge_blocks;      // ChargeBlock[ceil(n_pairs / 32)], zero-charge padded
     cpet::DevBuf raw_x, raw_q;       // staging for host uploads
     // scratch
-    cpet::DevBuf in0, in1, out0, out1, work0, work1, work2, counters;
+    cpet::DevBuf in0, in1, out0, out1, work0, work1, work2, counters, flags;
     cpet::Tuning tune;
     int64_t last_counters[3] = {0, 0, 0};
     double last_kernel_ms = 0.0;

@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(CPET_K2_MAXT, 1) k2w_topo_kernel(const K2WPara
                         const double ddx = (double)W.sx[q] - (double)nx;
                         const double ddy = (double)W.sy[q] - (double)ny;
                         const double ddz = (double)W.sz[q] - (double)nz;
-                        W.dist[q] = (float)sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+                        W.dist[q] = (float)sqrt_f64_fast(ddx * ddx + ddy * ddy + ddz * ddz);
                     }
                 }
                 W.ux[q] = ux; W.uy[q] = uy; W.uz[q] = uz;

@@ -44,7 +44,7 @@ def frame2a(golden):
 
 def reset_tuning(m):
     m.set_tuning(k1_threads=0, k1_points=0, k1_lanes=0, k1_tile_pairs=0, k1_stages=0, k1_splits=0,
-                 k1_lattice=-1,
+                 k1_lattice=-1, k1_softscan=-1,
                  k2_points=0, k2_threads=0, k2_lanes=0, k2_tile_pairs=0, k2_stages=0, k2_sort=-1,
                  k2_impl=0, k2_cap=0)
 
@@ -279,6 +279,41 @@ def test_field_lattice_matches_general_kernel(M, frame2a, shape):
                   f64.field_grid(bumped.reshape(-1, 3), x, Q, True)) < FIELD_TOL
 
 
+def test_field_lattice_softening_scan(M, frame2a):
+    """Softened meshes: when no charge lies within 1e-3 A of a node the unsoftened instantiation
+    serves the call (max(r^2, eps) == r^2 everywhere) -- same bits as the softened kernel; a charge
+    sitting on a node (r = 0, where only the softening keeps the field finite) switches back."""
+    x, Q = frame2a
+    xs = np.linspace(-0.5, 0.5, 11, dtype=np.float32)
+    ys = np.linspace(-0.4, 0.6, 9, dtype=np.float32)
+    zs = np.linspace(-0.7, 0.3, 13, dtype=np.float32)
+    reset_tuning(M)
+    try:
+        for case in ("clear", "on_node", "near_node"):
+            xc = x.copy()
+            if case == "on_node":
+                xc[17] = (xs[3], ys[4], zs[5])
+            elif case == "near_node":
+                xc[17] = (xs[3] + np.float32(4e-4), ys[4] - np.float32(3e-4), zs[5] + np.float32(2e-4))
+            M.set_charges(xc, Q)
+            M.set_tuning(k1_splits=1, k1_softscan=0)
+            want = M.field_lattice(xs, ys, zs, soften=True)
+            n0 = M.last_counters()["launches"]
+            M.set_tuning(k1_splits=1, k1_softscan=1)
+            got = M.field_lattice(xs, ys, zs, soften=True)
+            assert M.last_counters()["launches"] == n0 + 2       # scan + the instantiation that exits at once
+            np.testing.assert_array_equal(got, want)
+            assert np.isfinite(got).all()
+            raw = M.field_lattice(xs, ys, zs, soften=False)
+            if case == "clear":
+                np.testing.assert_array_equal(raw, want)
+            else:
+                assert not np.array_equal(raw, want)            # the softening did act
+    finally:
+        reset_tuning(M)
+        M.set_charges(x, Q)
+
+
 def test_field_grid_recognises_box_meshes(M, frame2a):
     """compute_looped_field only ever receives mesh.reshape(-1,3): the library detects the
     tensor-product structure on the device and switches kernels without changing a single bit."""
@@ -412,6 +447,28 @@ def test_topo_all_kernel_variants(M, golden, cfg):
             ok = np.abs(got[:, 0] - ref[:, 0]) < h / 2
             assert ok.mean() > 0.95
             assert np.max(np.abs(got[ok, 1] - ref[ok, 1])) <= 2 * curv_tol_sd(h)
+    finally:
+        reset_tuning(M)
+
+
+def test_topo_zero_charges_and_origin_seed(M):
+    """Exact zeros in Q (PQR files carry them) contribute exactly nothing; a seed at the origin is
+    not special."""
+    x, Q = synth.charges(3001, seed=11, box=0.5)
+    Q = Q.copy(); Q[::7] = 0.0
+    seeds, n_iter, dims, _ = synth.seeds(6, 0.5, 0.1)
+    seeds = np.vstack([np.zeros((1, 3), np.float32), seeds]).astype(np.float32)
+    n_iter = np.concatenate([[9], n_iter])
+    reset_tuning(M)
+    try:
+        want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
+        got, steps = M.topo_batch(seeds, n_iter, x, Q, 0.1, dims, want_steps=True)
+        check_lines(got, steps, want, wsteps, 0.1, curv_tol_dir(0.1))
+        keep = Q != 0.0
+        got2 = M.topo_batch(seeds, n_iter, x[keep], Q[keep], 0.1, dims)
+        same = np.abs(got2[:, 0] - got[:, 0]) < 0.05
+        assert same.mean() > 0.99
+        np.testing.assert_allclose(got2[same], got[same], rtol=0, atol=2e-5)
     finally:
         reset_tuning(M)
 

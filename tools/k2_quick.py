@@ -10,8 +10,7 @@ from pycpet_b200.device import Engine
 eng = Engine(0); eng.set_tuning(timing=1)
 CASES = [(7890, 47, 0.1), (7890, 100, 0.1), (7890, 18, 0.1), (30_000, 47, 0.1), (7890, 47, 0.01), (1000, 47, 0.1),
          (100_000, 30, 0.1)]
-CFGS = [dict(), dict(k2_cap=4), dict(k2_cap=2), dict(k2_cap=1), dict(k2_sort=0), dict(k2_threads=384),
-        dict(k2_impl=1), dict(k2_impl=1, k2_lanes=2), dict(k2_impl=1, k2_lanes=4)]
+CFGS = [dict(), dict(k2_cap=2), dict(k2_cap=1), dict(k2_impl=1)]
 if len(sys.argv) > 1:
     CFGS = [json.loads(a) for a in sys.argv[1:]]
 ref = {}
