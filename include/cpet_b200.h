@@ -68,9 +68,8 @@ int cpet_last_path(cpet_ctx *ctx);
  * "k1_lattice" (-1 auto-detect meshes in the host entry point, 0 off, 1 on),
  * "k1_softscan" (-1 auto, 0 off, 1 on: prove on the device that the softening cannot act on a mesh
  * and run the unsoftened kernel, bit-identical),
- * "k2_impl" (0 warp-wide streamline kernel, 1 slot kernel),"k2_cap" (warp-wide: lines per warp 1, 2, 4),
- * "k2_points" (slot kernel, lines per thread: 1, 2),"k2_lanes" (slot kernel, lanes per line: 1..32),
- * "k2_threads","k2_tile_pairs","k2_stages","k2_sort" (-1 auto, 0, 1),"timing" (record kernel events).
+ * "k2_cap" (streamlines per warp: 1, 2, 4),"k2_threads","k2_tile_pairs","k2_stages" (a tile size or
+ * stage count forces the streamed charge ring),"k2_sort" (-1 auto, 0, 1),"timing" (record kernel events).
  * value <= 0 restores the built-in heuristic (except the three-state keys). */
 int cpet_set_tuning(cpet_ctx *ctx, const char *key, int value);
 /* Counters of the last kernel-launching call: [0]=kernels launched, [1]=pair evaluations

@@ -188,8 +188,8 @@ int cpet_set_tuning(cpet_ctx* c, const char* key, int value) {
     struct { const char* k; int* v; } tab[] = {
         {"k1_threads", &t.k1_threads}, {"k1_points", &t.k1_points}, {"k1_lanes", &t.k1_lanes},
         {"k1_tile_pairs", &t.k1_tile_pairs}, {"k1_stages", &t.k1_stages}, {"k1_splits", &t.k1_splits}, {"k1_lattice", &t.k1_lattice}, {"k1_unroll", &t.k1_unroll}, {"k1_softscan", &t.k1_softscan},
-        {"k2_points", &t.k2_points}, {"k2_threads", &t.k2_threads}, {"k2_lanes", &t.k2_lanes}, {"k2_tile_pairs", &t.k2_tile_pairs},
-        {"k2_stages", &t.k2_stages}, {"k2_sort", &t.k2_sort}, {"k2_impl", &t.k2_impl}, {"k2_cap", &t.k2_cap},
+        {"k2_threads", &t.k2_threads}, {"k2_tile_pairs", &t.k2_tile_pairs},
+        {"k2_stages", &t.k2_stages}, {"k2_sort", &t.k2_sort}, {"k2_cap", &t.k2_cap},
         {"timing", &t.timing},
     };
     for (auto& e : tab) {

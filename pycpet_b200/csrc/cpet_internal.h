@@ -46,10 +46,9 @@ struct Tuning {
     int k1_unroll = 0;     // lattice kernel inner-loop unroll (1, 2 or 4; 0 = default 2)
     int k1_lattice = -1;   // -1 auto (detect z-fastest tensor-product meshes in the host entry point), 0 off, 1 on
     int k1_softscan = -1;  // lattice kernel: -1 auto (scan for charges on grid nodes when the mesh is large), 0 off, 1 on
-    int k2_points = 0, k2_threads = 0, k2_lanes = 0, k2_tile_pairs = 0, k2_stages = 0;
+    int k2_threads = 0, k2_tile_pairs = 0, k2_stages = 0;
     int k2_sort = -1;   // -1 heuristic (on), 0 off, 1 on
-    int k2_impl = 0;    // 0 warp-wide kernel (default), 1 slot kernel (G lanes per line)
-    int k2_cap = 0;     // warp-wide kernel: streamlines per warp (1, 2, 4; 0 = heuristic)
+    int k2_cap = 0;     // streamlines per warp (1, 2, 4; 0 = heuristic)
     int timing = 0;
 };
 

@@ -28,9 +28,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = Engine(local)
-    # the launch heuristics depend on the shard size (lanes per point/line, charge splits), which
-    # changes the order of the FP64 partial sums; pin them so sharded == unsharded bit for bit
-    eng.set_tuning(k1_lanes=8, k1_splits=1, k2_lanes=8, k2_threads=256)
+    # K1's launch heuristics depend on the shard size (lanes per point, charge splits), which changes
+    # the order of the FP64 partial sums; pin them so sharded == unsharded bit for bit.  The streamline
+    # kernel sums every line in the same order whatever the shard size.
+    eng.set_tuning(k1_lanes=8, k1_splits=1)
     x, Q = synth.charges(7890, seed=1, box=0.5)
     eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
 

@@ -45,8 +45,7 @@ def frame2a(golden):
 def reset_tuning(m):
     m.set_tuning(k1_threads=0, k1_points=0, k1_lanes=0, k1_tile_pairs=0, k1_stages=0, k1_splits=0,
                  k1_lattice=-1, k1_softscan=-1,
-                 k2_points=0, k2_threads=0, k2_lanes=0, k2_tile_pairs=0, k2_stages=0, k2_sort=-1,
-                 k2_impl=0, k2_cap=0)
+                 k2_threads=0, k2_tile_pairs=0, k2_stages=0, k2_sort=-1, k2_cap=0)
 
 
 # ------------------------------------------------------------------------------------ K1 --------
@@ -413,20 +412,10 @@ def test_topo_example_3A(M, golden, frame2a):
 
 
 @pytest.mark.parametrize("cfg", [
-    # warp-wide kernel (default): lines per warp, charge residency, thread counts, queue order
+    # lines per warp, charge residency, thread counts, queue order
     dict(), dict(k2_cap=1), dict(k2_cap=2), dict(k2_cap=4), dict(k2_cap=4, k2_threads=64, k2_sort=1),
     dict(k2_cap=2, k2_sort=0), dict(k2_cap=4, k2_tile_pairs=256, k2_stages=2),   # streamed charge ring
     dict(k2_cap=1, k2_tile_pairs=64, k2_stages=4), dict(k2_cap=2, k2_tile_pairs=512, k2_stages=3, k2_threads=128),
-    # slot kernel (k2_impl=1): G lanes per line, P lines per thread
-    dict(k2_impl=1, k2_lanes=1), dict(k2_impl=1, k2_lanes=2), dict(k2_impl=1, k2_lanes=4),
-    dict(k2_impl=1, k2_lanes=8), dict(k2_impl=1, k2_lanes=16), dict(k2_impl=1, k2_lanes=32),
-    dict(k2_impl=1, k2_lanes=1, k2_threads=64, k2_sort=1), dict(k2_impl=1, k2_lanes=4, k2_sort=0),
-    dict(k2_impl=1, k2_lanes=1, k2_tile_pairs=256, k2_stages=2),
-    dict(k2_impl=1, k2_lanes=8, k2_tile_pairs=512, k2_stages=3, k2_threads=128),
-    dict(k2_impl=1, k2_lanes=32, k2_tile_pairs=64, k2_stages=4),
-    dict(k2_impl=1, k2_points=2, k2_lanes=1), dict(k2_impl=1, k2_points=2, k2_lanes=2, k2_threads=256),
-    dict(k2_impl=1, k2_points=2, k2_lanes=8, k2_sort=0),
-    dict(k2_impl=1, k2_points=2, k2_lanes=4, k2_tile_pairs=128, k2_stages=2),
 ])
 def test_topo_all_kernel_variants(M, golden, cfg):
     g = golden("synthetic_math_ops.npz")

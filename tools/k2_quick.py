@@ -1,6 +1,5 @@
 #!/usr/bin/env python
-"""Quick K2 timing of the bench cases: warp-wide kernel (default) against the slot kernel, with a
-few overrides.  Kernel time only (CUDA events around the integrator launch), best of 3."""
+"""Quick K2 timing of the bench cases with the default heuristics and a few overrides.  Kernel time only (CUDA events around the integrator launch), best of 3."""
 import os, sys, json
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,7 +9,7 @@ from pycpet_b200.device import Engine
 eng = Engine(0); eng.set_tuning(timing=1)
 CASES = [(7890, 47, 0.1), (7890, 100, 0.1), (7890, 18, 0.1), (30_000, 47, 0.1), (7890, 47, 0.01), (1000, 47, 0.1),
          (100_000, 30, 0.1)]
-CFGS = [dict(), dict(k2_cap=2), dict(k2_cap=1), dict(k2_impl=1)]
+CFGS = [dict(), dict(k2_cap=4), dict(k2_cap=2), dict(k2_cap=1), dict(k2_sort=0)]
 if len(sys.argv) > 1:
     CFGS = [json.loads(a) for a in sys.argv[1:]]
 ref = {}
@@ -21,7 +20,7 @@ for m, n_axis, h in CASES:
     eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
     base = None
     for cfg in CFGS:
-        eng.set_tuning(k2_points=0, k2_lanes=0, k2_threads=0, k2_impl=0, k2_cap=0, k2_sort=-1)
+        eng.set_tuning(k2_threads=0, k2_cap=0, k2_sort=-1)
         eng.set_tuning(**cfg)
         best = 1e30
         for _ in range(3):

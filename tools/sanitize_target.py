@@ -22,12 +22,12 @@ for M_ in (301, 20_000):                       # resident and streamed charge st
         m.field_grid(pts[:333] * np.float32(0.9), soften=True)
     m.set_tuning(k1_points=0, k1_lanes=0, k1_splits=0, k1_tile_pairs=0, k1_stages=0)
     seeds, n_iter, dims, _ = synth.seeds(6, 0.5, 0.1)
-    for cfg in (dict(), dict(k2_lanes=1), dict(k2_lanes=4, k2_points=2), dict(k2_lanes=32, k2_tile_pairs=64, k2_stages=2)):
-        m.set_tuning(k2_points=0, k2_lanes=0, k2_tile_pairs=0, k2_stages=0)
+    for cfg in (dict(), dict(k2_cap=1), dict(k2_cap=2, k2_threads=128), dict(k2_cap=4, k2_tile_pairs=64, k2_stages=2)):
+        m.set_tuning(k2_cap=0, k2_threads=0, k2_tile_pairs=0, k2_stages=0)
         m.set_tuning(**cfg)
         rows, steps = m.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, want_steps=True)
         m.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, second_diff=True)
-    m.set_tuning(k2_points=0, k2_lanes=0, k2_tile_pairs=0, k2_stages=0)
+    m.set_tuning(k2_cap=0, k2_threads=0, k2_tile_pairs=0, k2_stages=0)
     de, ce = np.linspace(0, 1.8, 21), np.linspace(0, 5, 31)
     m.hist2d(rows, de, ce)
     m.topo_hist(seeds, n_iter, de, ce, step_size=0.1, dimensions=dims)

@@ -68,24 +68,19 @@ def main():
             sd = torch.from_numpy(seeds).cuda()
             ni = torch.from_numpy(n_iter.astype(np.int32)).cuda()
             eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
-            for P, G, thr, srt in itertools.product((1, 2), (0, 1, 2, 4, 8, 32), (128, 256, 512), (1, 0)):
-                if srt == 0 and (G not in (0, 1) or thr != 256):
+            for cap, thr, srt in itertools.product((0, 1, 2, 4), (256, 384, 512), (1, 0)):
+                if srt == 0 and (cap != 0 or thr != 512):
                     continue
-                if G == 0 and thr != 256:
-                    continue
-                if G >= 8 and thr == 128:
-                    continue
-                eng.set_tuning(k2_points=P, k2_lanes=G, k2_threads=(0 if G == 0 else thr),
-                               k2_sort=(-1 if G == 0 else srt))
+                eng.set_tuning(k2_cap=cap, k2_threads=thr, k2_sort=(-1 if cap == 0 else srt))
                 ms = timed(eng, lambda: eng.topo_batch(sd, ni, h, dims), reps=2)
                 c = eng.last_counters()
                 rate = c["pair_evals"] / (ms * 1e-3)
-                rec = dict(kernel="k2", M=len(Q), L=len(seeds), h=h, P=P, G=G, threads=thr, sort=srt, ms=ms,
+                rec = dict(kernel="k2", M=len(Q), L=len(seeds), h=h, cap=cap, threads=thr, sort=srt, ms=ms,
                            field_evals=c["field_evals"], pairs_per_s=rate, lines_per_s=len(seeds) / (ms * 1e-3),
                            frac_nominal_fp32=rate * 20 / 1e12 / PEAK_NOMINAL)
                 res.append(rec)
                 print(json.dumps(rec), flush=True)
-        eng.set_tuning(k2_points=0, k2_lanes=0, k2_threads=0, k2_sort=-1)
+        eng.set_tuning(k2_cap=0, k2_threads=0, k2_sort=-1)
 
     out["results"] = res
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
