@@ -167,6 +167,21 @@ int cpet_topo_hist(cpet_ctx *ctx, int n_lines, const float *seeds, const int32_t
                    int32_t *steps, int nd, const double *d_edges, int nc, const double *c_edges,
                    int64_t *counts);
 
+/* MD-frame batch (BASELINE "1000 frames x topology"; in the reference one CPET.run() iteration per
+ * PDB file, TOP:96-127, each ending in compute_topo_complete_c_shared SC:675-712, and later
+ * make_histograms over the .top files UC:596-718).  The frames share seeds (n_lines,3), box, step
+ * and bin edges; frame f has its own charge set x[f] (n_charges[f],3), Q[f] (n_charges[f],) and,
+ * when n_iter_frame_stride != 0, its own n_iter row at n_iter + f*n_iter_frame_stride (0 = one row
+ * shared by all frames).  counts is (n_frames,nd,nc) int64; out_rows is (n_frames,n_lines,2) f32 or
+ * NULL.  Frames alternate between two internal streams, so the host<->device copies of one frame
+ * overlap the kernels of its neighbours; pass pinned host memory for that overlap to be real.
+ * Every frame's result is identical to a cpet_topo_hist call on that frame alone. */
+int cpet_topo_hist_frames(cpet_ctx *ctx, int n_frames, const int *n_charges, const float *const *x,
+                          const float *const *Q, int n_lines, const float *seeds,
+                          const int32_t *n_iter, int64_t n_iter_frame_stride, float step_size,
+                          const float dims[3], unsigned flags, float *out_rows, int nd,
+                          const double *d_edges, int nc, const double *c_edges, int64_t *counts);
+
 /* Exact order statistics of float32 values on the device: out[t] = the ranks[t]-th smallest
  * (0-based) of values[i*stride + offset], i < n, NaNs ordered last as NumPy sorts them.  Rank 0 and
  * n-1 give the global min / max, the neighbours of 0.25(n-1) and 0.75(n-1) give scipy.stats.iqr,

@@ -72,6 +72,9 @@ SIGNATURES = {
                                 c_void_p, c_void_p]),
     "cpet_topo_hist": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_uint, c_void_p,
                                c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "cpet_topo_hist_frames": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                      c_int64, c_float, c_void_p, c_uint, c_void_p, c_int, c_void_p, c_int,
+                                      c_void_p, c_void_p]),
     "cpet_order_stats": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpet_order_stats_dev": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpet_radix_hist_dev": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

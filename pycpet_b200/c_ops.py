@@ -233,6 +233,46 @@ class Math_ops:
             ptr(rows) if want_rows else None, None, nd, ptr(de), nc, ptr(ce), ptr(counts)))
         return rows, counts
 
+    def topo_hist_frames(self, frames, seeds, n_iter, d_edges, c_edges, step_size=0.1,
+                         dimensions=(1, 1, 1), second_diff=False, want_rows=False, rows_out=None,
+                         counts_out=None):
+        """A batch of MD frames sharing seeds, box, step and bin edges.  `frames` is a sequence of
+        (x (M_f,3), Q (M_f,)) pairs; `n_iter` is (L,) shared by all frames or (F,L) per frame.
+        -> (rows (F,L,2) float32 or None, counts (F,nd,nc) int64); copies and kernels of neighbouring
+        frames overlap (two internal streams).  Frame by frame identical to topo_hist()."""
+        seeds = f32c(seeds, (-1, 3))
+        n = seeds.shape[0]
+        F = len(frames)
+        xs = [f32c(fx, (-1, 3)) for fx, _ in frames]
+        qs = [f32c(np.asarray(fq).reshape(-1)) for _, fq in frames]
+        for fx, fq in zip(xs, qs):
+            if fx.shape[0] != fq.shape[0]:
+                raise ValueError(f"x has {fx.shape[0]} rows but Q has {fq.shape[0]} entries")
+        n_iter = np.ascontiguousarray(np.asarray(n_iter), dtype=np.int32)
+        if n_iter.ndim == 1:
+            if n_iter.shape[0] != n:
+                raise ValueError(f"{n} seeds but {n_iter.shape[0]} n_iter entries")
+            stride = 0
+        else:
+            if n_iter.shape != (F, n):
+                raise ValueError(f"n_iter must be ({n},) or ({F},{n}), got {n_iter.shape}")
+            stride = n
+        dims = f32c(dimensions, (3,))
+        de = np.ascontiguousarray(d_edges, dtype=np.float64)
+        ce = np.ascontiguousarray(c_edges, dtype=np.float64)
+        nd, nc = de.shape[0] - 1, ce.shape[0] - 1
+        rows = self._out(rows_out, (F, n, 2), np.float32) if want_rows else None
+        counts = self._out(counts_out, (F, nd, nc), np.int64)
+        m_arr = np.array([fx.shape[0] for fx in xs], dtype=np.int32)
+        xp = (ctypes.c_void_p * max(F, 1))(*[fx.ctypes.data for fx in xs])
+        qp = (ctypes.c_void_p * max(F, 1))(*[fq.ctypes.data for fq in qs])
+        check(self.math.cpet_topo_hist_frames(
+            self.ctx, F, ptr(m_arr), ctypes.cast(xp, ctypes.c_void_p), ctypes.cast(qp, ctypes.c_void_p),
+            n, ptr(seeds), ptr(n_iter), stride, float(step_size), ptr(dims),
+            _lib.CPET_TOPO_CURV_SECOND_DIFF if second_diff else 0,
+            ptr(rows) if want_rows else None, nd, ptr(de), nc, ptr(ce), ptr(counts)))
+        return rows, counts
+
     def hist2d(self, values, d_edges, c_edges):
         """Batched np.histogram2d counts.  values: (F, n, 2) or (n, 2), float64 or float32.
         -> (F, nd, nc) (or (nd, nc)) int64."""

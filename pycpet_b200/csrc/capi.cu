@@ -168,6 +168,8 @@ int cpet_destroy(cpet_ctx* c) {
         if (c->ev0[i]) cudaEventDestroy(c->ev0[i]);
         if (c->ev1[i]) cudaEventDestroy(c->ev1[i]);
     }
+    for (int i = 0; i < 2; ++i)
+        if (c->pipe[i]) { cpet_destroy(c->pipe[i]); c->pipe[i] = nullptr; }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return CPET_OK;
@@ -539,6 +541,107 @@ int cpet_topo_hist(cpet_ctx* c, int n_lines, const float* seeds, const int32_t* 
         CPET_CUDA_TRY(cudaMemcpyAsync(steps, c->out1.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaMemcpyAsync(counts, c->work0.p, cbytes, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CPET_OK;
+}
+
+// ---------------------------------------------------------------- MD-frame batch -----------
+// Two child contexts (own streams, own staging buffers) take the frames alternately: everything a
+// frame needs is enqueued on its child's stream -- H2D of its charges (and n_iter), pack, queue sort,
+// integrator, histogram, D2H of its counts (and rows) -- so the copies of frame f+1 / f-1 overlap
+// the kernels of frame f, and the CTAs of frame f+1 start on each SM as soon as frame f leaves it.
+__global__ void add_evals_kernel(const unsigned long long* __restrict__ evals, int n_charges,
+                                 unsigned long long* __restrict__ totals) {
+    totals[0] += *evals;
+    totals[1] += *evals * (unsigned long long)n_charges;
+}
+
+static int frames_child(cpet_ctx* c, int i, cpet_ctx** out) {
+    if (!c->pipe[i]) {
+        if (int rc = make_ctx(c->device, nullptr, false, &c->pipe[i])) return rc;
+    }
+    c->pipe[i]->tune = c->tune;
+    c->pipe[i]->tune.timing = 0;
+    *out = c->pipe[i];
+    return CPET_OK;
+}
+
+int cpet_topo_hist_frames(cpet_ctx* c, int n_frames, const int* n_charges, const float* const* x,
+                          const float* const* Q, int n_lines, const float* seeds, const int32_t* n_iter,
+                          int64_t n_iter_frame_stride, float step_size, const float dims[3], unsigned flags,
+                          float* out_rows, int nd, const double* d_edges, int nc, const double* c_edges,
+                          int64_t* counts) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_frames >= 0 && n_lines >= 0, CPET_ERR_INVALID, "negative sizes");
+    CPET_REQUIRE((flags & ~CPET_TOPO_CURV_SECOND_DIFF) == 0, CPET_ERR_INVALID, "unknown flag bits 0x%x", flags);
+    CPET_REQUIRE(dims != nullptr, CPET_ERR_INVALID, "dims is NULL");
+    CPET_REQUIRE(nd >= 1 && nc >= 1 && d_edges && c_edges, CPET_ERR_INVALID, "histogram needs edges, nd >= 1 and nc >= 1");
+    CPET_REQUIRE(n_frames == 0 || (n_charges && x && Q && counts), CPET_ERR_INVALID, "NULL frame arrays");
+    CPET_REQUIRE(n_lines == 0 || (seeds && n_iter), CPET_ERR_INVALID, "NULL seed/n_iter arrays");
+    CPET_REQUIRE(n_iter_frame_stride == 0 || n_iter_frame_stride >= n_lines, CPET_ERR_INVALID,
+                 "n_iter_frame_stride must be 0 (shared) or >= n_lines");
+    c->last_counters[0] = c->last_counters[1] = c->last_counters[2] = 0;
+    if (n_frames == 0) return CPET_OK;
+    for (int f = 0; f < n_frames; ++f)
+        CPET_REQUIRE(n_charges[f] >= 0 && (n_charges[f] == 0 || (x[f] && Q[f])), CPET_ERR_INVALID,
+                     "frame %d: bad charge arrays", f);
+
+    const size_t n = (size_t)(n_lines > 0 ? n_lines : 1);
+    const size_t cbytes = sizeof(int64_t) * (size_t)nd * nc;
+    const int n_children = n_frames > 1 ? 2 : 1;
+    cpet_ctx* ch[2] = {nullptr, nullptr};
+    const double* dd[2]; const double* dc[2];
+    for (int i = 0; i < n_children; ++i) {
+        if (int rc = frames_child(c, i, &ch[i])) return rc;
+        cpet_ctx* k = ch[i];
+        if (int rc = upload_edges(k, nd, d_edges, nc, c_edges, &dd[i], &dc[i])) return rc;
+        if (int rc = k->in0.reserve(sizeof(float) * 3 * n)) return rc;
+        if (int rc = k->in1.reserve(sizeof(int32_t) * n)) return rc;
+        if (int rc = k->out0.reserve(sizeof(float) * 2 * n)) return rc;
+        if (int rc = k->work0.reserve(cbytes)) return rc;
+        if (int rc = k->flags.reserve(64)) return rc;
+        CPET_CUDA_TRY(cudaMemsetAsync(k->flags.p, 0, 64, k->stream));
+        if (n_lines > 0) {
+            CPET_CUDA_TRY(cudaMemcpyAsync(k->in0.p, seeds, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, k->stream));
+            if (n_iter_frame_stride == 0)
+                CPET_CUDA_TRY(cudaMemcpyAsync(k->in1.p, n_iter, sizeof(int32_t) * n, cudaMemcpyHostToDevice, k->stream));
+        }
+    }
+    int64_t launches = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        cpet_ctx* k = ch[f % n_children];
+        const double* kd = dd[f % n_children];
+        const double* kc = dc[f % n_children];
+        if (int rc = cpet_set_charges(k, n_charges[f], x[f], Q[f])) return rc;
+        launches += 1;
+        if (n_lines > 0) {
+            if (n_iter_frame_stride != 0)
+                CPET_CUDA_TRY(cudaMemcpyAsync(k->in1.p, n_iter + (size_t)f * (size_t)n_iter_frame_stride,
+                                              sizeof(int32_t) * n, cudaMemcpyHostToDevice, k->stream));
+            if (int rc = launch_topo(k, n_lines, k->in0.as<float>(), k->in1.as<int32_t>(), step_size, dims, flags,
+                                     k->out0.as<float>(), nullptr))
+                return rc;
+            launches += k->last_counters[0];
+            add_evals_kernel<<<1, 1, 0, k->stream>>>(
+                reinterpret_cast<const unsigned long long*>(k->counters.as<unsigned char>() + 8), k->n_charges,
+                k->flags.as<unsigned long long>());
+            CPET_CUDA_TRY(cudaGetLastError());
+        }
+        if (int rc = launch_hist2d(k, 1, n_lines, k->out0.p, false, nd, kd, nc, kc, k->work0.as<unsigned long long>()))
+            return rc;
+        launches += k->last_counters[0];
+        if (n_lines > 0 && out_rows)
+            CPET_CUDA_TRY(cudaMemcpyAsync(out_rows + (size_t)f * 2 * n, k->out0.p, sizeof(float) * 2 * n,
+                                          cudaMemcpyDeviceToHost, k->stream));
+        CPET_CUDA_TRY(cudaMemcpyAsync(counts + (size_t)f * nd * nc, k->work0.p, cbytes, cudaMemcpyDeviceToHost, k->stream));
+    }
+    unsigned long long tot[2][2] = {{0, 0}, {0, 0}};
+    for (int i = 0; i < n_children; ++i) {
+        CPET_CUDA_TRY(cudaMemcpyAsync(tot[i], ch[i]->flags.p, sizeof(tot[i]), cudaMemcpyDeviceToHost, ch[i]->stream));
+        CPET_CUDA_TRY(cudaStreamSynchronize(ch[i]->stream));
+    }
+    c->last_counters[0] = launches;
+    c->last_counters[2] = (int64_t)(tot[0][0] + tot[1][0]);
+    c->last_counters[1] = (int64_t)(tot[0][1] + tot[1][1]);
     return CPET_OK;
 }
 

@@ -78,6 +78,7 @@ struct cpet_ctx {
     static constexpr int kTimerRing = 256;
     cudaEvent_t ev0[kTimerRing] = {}, ev1[kTimerRing] = {};
     int timer_count = 0;      // launches recorded since the last cpet_kernel_times()
+    cpet_ctx* pipe[2] = {nullptr, nullptr};   // child contexts of cpet_topo_hist_frames (own streams)
 };
 
 namespace cpet {

@@ -701,6 +701,44 @@ def test_topo_hist_fused_call(M, frame2a):
 
 
 # --------------------------------------------------------------------------- legacy symbols -----
+def test_topo_hist_frames_matches_single_frame_calls(M):
+    """The MD-frame batch call (two internal streams) returns, frame by frame, exactly what
+    topo_hist returns for that frame alone: shared and per-frame n_iter, different charge counts per
+    frame (one of them streaming its charges), F = 1 and F = 0."""
+    seeds, n_iter, dims, max_steps = synth.seeds(9, 0.5, 0.1)
+    L = len(seeds)
+    de, ce = np.linspace(0, 1.7, 31), np.linspace(0, 4.0, 41)
+    rng = np.random.default_rng(5)
+    frames = []
+    for f, m_f in enumerate([3000, 2999, 30001, 1, 7890]):
+        x, Q = synth.charges(m_f, seed=20 + f, box=0.5)
+        frames.append((x, Q))
+    nit_frames = rng.integers(1, max_steps, size=(len(frames), L)).astype(np.int32)
+    reset_tuning(M)
+    for nit in (n_iter, nit_frames):
+        rows, counts = M.topo_hist_frames(frames, seeds, nit, de, ce, step_size=0.1, dimensions=dims,
+                                          want_rows=True)
+        c = M.last_counters()
+        evals = 0
+        for f, (x, Q) in enumerate(frames):
+            nf = nit if np.ndim(nit) == 1 else nit[f]
+            r1, c1 = M.topo_hist(seeds, nf, de, ce, x=x, Q=Q, step_size=0.1, dimensions=dims)
+            evals += M.last_counters()["pair_evals"]
+            np.testing.assert_array_equal(rows[f], r1)
+            np.testing.assert_array_equal(counts[f], c1)
+        assert c["pair_evals"] == evals
+        _, counts_only = M.topo_hist_frames(frames, seeds, nit, de, ce, step_size=0.1, dimensions=dims)
+        np.testing.assert_array_equal(counts_only, counts)
+    rows1, counts1 = M.topo_hist_frames(frames[:1], seeds, n_iter, de, ce, step_size=0.1, dimensions=dims,
+                                        want_rows=True)
+    np.testing.assert_array_equal(rows1[0], M.topo_hist(seeds, n_iter, de, ce, x=frames[0][0], Q=frames[0][1],
+                                                        step_size=0.1, dimensions=dims)[0])
+    rows0, counts0 = M.topo_hist_frames([], seeds, n_iter, de, ce, step_size=0.1, dimensions=dims, want_rows=True)
+    assert rows0.shape == (0, L, 2) and counts0.shape == (0, 30, 40)
+    with pytest.raises(ValueError):
+        M.topo_hist_frames(frames, seeds, nit_frames[:2], de, ce, step_size=0.1, dimensions=dims)
+
+
 def test_legacy_symbols(M, golden):
     g = golden("synthetic_math_ops.npz")
     x, Q, pts = g["x"], g["Q"], g["points"]
