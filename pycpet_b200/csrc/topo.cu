@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(CPET_K2_MAXT, 1) k2w_topo_kernel(const K2WPara
                 if (base + (unsigned)want >= (unsigned)prm.n_lines) exhausted = true;
             }
         }
-        const unsigned am = __ballot_sync(0xffffffffu, owner && W.line[lane] >= 0);   // also orders the stores above
+        __syncwarp();     // the owners' stores above must be visible to every lane's gather below
+        const unsigned am = __ballot_sync(0xffffffffu, owner && W.line[lane] >= 0);
         bool go;
         if (prm.resident) go = (am != 0u);
         else go = __syncthreads_or(am != 0u ? 1 : 0) != 0;

@@ -21,6 +21,10 @@ for M_ in (301, 20_000):                       # resident and streamed charge st
         m.set_tuning(**cfg)
         m.field_grid(pts[:333] * np.float32(0.9), soften=True)
     m.set_tuning(k1_points=0, k1_lanes=0, k1_splits=0, k1_tile_pairs=0, k1_stages=0)
+    ax = np.linspace(-0.5, 0.5, 9, dtype=np.float32)
+    m.set_tuning(k1_softscan=1)                # scan + both lattice instantiations (one exits at once)
+    m.field_lattice(ax, ax, ax, soften=True)
+    m.set_tuning(k1_softscan=-1)
     seeds, n_iter, dims, _ = synth.seeds(6, 0.5, 0.1)
     for cfg in (dict(), dict(k2_cap=1), dict(k2_cap=2, k2_threads=128), dict(k2_cap=4, k2_tile_pairs=64, k2_stages=2)):
         m.set_tuning(k2_cap=0, k2_threads=0, k2_tile_pairs=0, k2_stages=0)
@@ -33,6 +37,9 @@ for M_ in (301, 20_000):                       # resident and streamed charge st
     m.topo_hist(seeds, n_iter, de, ce, step_size=0.1, dimensions=dims)
     m.hist2d(np.random.default_rng(0).random((3, 1000, 2)), np.linspace(0, 1, 301), np.linspace(0, 1, 401))
     m.order_stats(rows, [0, 10, len(rows) - 1], column=1)
+frames = [synth.charges(n_f, seed=3 + n_f, box=0.5) for n_f in (500, 20_001, 77)]
+m.topo_hist_frames(frames, seeds, n_iter, np.linspace(0, 1.8, 21), np.linspace(0, 5, 31), step_size=0.1,
+                   dimensions=dims, want_rows=True)
 H = np.random.default_rng(1).random((5, 100)); H /= H.sum(1, keepdims=True)
 m.chi2_matrix(H)
 m.calc_field(np.zeros(3, np.float32), x, Q); m.calc_esp_base(np.zeros(3, np.float32), x, Q)
