@@ -37,8 +37,8 @@ def ncu_md(rep, out, title):
     idx = {h: i for i, h in enumerate(hdr)}
     stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")]
     md = [f"# {title}\n",
-          "Captured with `ncu --set full --clock-control none --import-source on -k regex:\"k1_grid|k2_topo|k1_lattice\" "
-          "-c 5 python tools/prof_target.py all 1` (M = 7,890 charges; K1 on a 101^3 grid, K2 on the 3A line set 47^3).",
+          "Captured with `ncu --set full --clock-control none --import-source on -k regex:\"k1_grid|k2w_topo|k1_lattice\" "
+          "-c 8 python tools/prof_target.py all 1` (M = 7,890 charges; K1 on a 101^3 grid, K2 on the 3A line set 47^3).",
           "Numbers under ncu are for pipe utilisation, stall reasons and DRAM traffic only; throughput is quoted from "
           "bench.py / tools/sweep.py (CUDA events, no profiler).\n"]
     for r in rows[2:]:

@@ -20,11 +20,17 @@ eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
 if which in ("all", "k1"):
     pts = torch.from_numpy(synth.grid(101, 0.5)).cuda()
     ax = torch.linspace(-0.5, 0.5, 101, device="cuda")
+    eng.set_tuning(k1_lattice=0)                      # general kernels on the flat point list
     for _ in range(reps):
         eng.field_grid(pts, soften=False)
         eng.field_grid(pts, soften=True)
         eng.esp_grid(pts)
-        eng.field_lattice(ax, ax, ax, soften=True)
+    eng.set_tuning(k1_lattice=-1)
+    for _ in range(reps):
+        eng.field_lattice(ax, ax, ax, soften=True)    # softening scan -> unsoftened instantiation serves the call
+        eng.set_tuning(k1_softscan=0)
+        eng.field_lattice(ax, ax, ax, soften=True)    # softened instantiation
+        eng.set_tuning(k1_softscan=-1)
 if which in ("all", "k2"):
     seeds, n_iter, dims, _ = synth.seeds(47, 0.5, 0.1)
     sd = torch.from_numpy(seeds).cuda()
