@@ -262,6 +262,11 @@ __global__ void __launch_bounds__(256) soften_scan_kernel(const ChargePair* __re
                                                           const float* __restrict__ zs, int nz,
                                                           unsigned* __restrict__ flag) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    // a NaN node coordinate makes r^2 NaN, which fmaxf(r^2, eps) turns into eps: keep the softened kernel
+    if (j < nx + ny + nz) {
+        const float a = j < nx ? xs[j] : (j < nx + ny ? ys[j - nx] : zs[j - nx - ny]);
+        if (a != a) *flag = 1u;
+    }
     if (j >= n_pairs) return;
     // |d| >= 1.0005e-3 on one axis => fl(d)^2 > 1e-6 => r^2 > eps whatever the other axes are
     const float T = 1.0005e-3f;
@@ -273,12 +278,14 @@ __global__ void __launch_bounds__(256) soften_scan_kernel(const ChargePair* __re
     bool hit = false;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+        const float sum = cx[h] + cy[h] + cz[h];
+        if (sum != sum) { hit = true; continue; }          // NaN (or inf - inf) charge coordinate: see above
         bool near_x = false, near_y = false, near_z = false;
-        for (int i = 0; i < nx; ++i) near_x = near_x || (fabsf(__ldg(xs + i) + cx[h]) < T);
+        for (int i = 0; i < nx; ++i) near_x = near_x || !(fabsf(__ldg(xs + i) + cx[h]) >= T);
         if (!near_x) continue;
-        for (int i = 0; i < ny; ++i) near_y = near_y || (fabsf(__ldg(ys + i) + cy[h]) < T);
+        for (int i = 0; i < ny; ++i) near_y = near_y || !(fabsf(__ldg(ys + i) + cy[h]) >= T);
         if (!near_y) continue;
-        for (int i = 0; i < nz; ++i) near_z = near_z || (fabsf(__ldg(zs + i) + cz[h]) < T);
+        for (int i = 0; i < nz; ++i) near_z = near_z || !(fabsf(__ldg(zs + i) + cz[h]) >= T);
         hit = hit || near_z;
     }
     if (hit) *flag = 1u;
@@ -479,7 +486,7 @@ int launch_field_lattice(cpet_ctx* c, int mode, int nx, int ny, int nz, const fl
     if (scan && c->n_pairs > 0) {
         if (int rc = c->flags.reserve(64)) return rc;
         CPET_CUDA_TRY(cudaMemsetAsync(c->flags.p, 0, 64, c->stream));
-        soften_scan_kernel<<<(c->n_pairs + 255) / 256, 256, 0, c->stream>>>(
+        soften_scan_kernel<<<((c->n_pairs > nx + ny + nz ? c->n_pairs : nx + ny + nz) + 255) / 256, 256, 0, c->stream>>>(
             c->charges.as<ChargePair>(), c->n_pairs, d_xs, nx, d_ys, ny, d_zs, nz, c->flags.as<unsigned>());
         CPET_CUDA_TRY(cudaGetLastError());
         prm.soft_flag = c->flags.as<unsigned>();

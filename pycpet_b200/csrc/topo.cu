@@ -537,6 +537,10 @@ static int launch_topo_warpwide(cpet_ctx* c, int n_lines, const float* d_seeds, 
     threads = (threads / 32) * 32;
     if (threads < 32) threads = 32;
     if (threads > CPET_K2_MAXT) threads = CPET_K2_MAXT;
+    if (tu.k2_threads <= 0 && (long long)n_lines < (long long)sms * (threads / 32)) {
+        // fewer lines than warps on the chip: one line per warp, spread over all SMs
+        threads = 32 * ((n_lines + sms - 1) / sms);
+    }
     const int warps_per_cta = threads / 32;
     const size_t hdr = 128 + sizeof(WarpLines) * (size_t)warps_per_cta;   // barriers + per-warp line state
 

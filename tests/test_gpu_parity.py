@@ -288,8 +288,10 @@ def test_field_lattice_softening_scan(M, frame2a):
     zs = np.linspace(-0.7, 0.3, 13, dtype=np.float32)
     reset_tuning(M)
     try:
-        for case in ("clear", "on_node", "near_node"):
+        for case in ("clear", "on_node", "near_node", "nan_charge"):
             xc = x.copy()
+            if case == "nan_charge":       # fmaxf(NaN, eps) = eps: only the softened kernel reproduces that
+                xc[17, 1] = np.nan
             if case == "on_node":
                 xc[17] = (xs[3], ys[4], zs[5])
             elif case == "near_node":
@@ -302,6 +304,8 @@ def test_field_lattice_softening_scan(M, frame2a):
             got = M.field_lattice(xs, ys, zs, soften=True)
             assert M.last_counters()["launches"] == n0 + 2       # scan + the instantiation that exits at once
             np.testing.assert_array_equal(got, want)
+            if case == "nan_charge":
+                continue
             assert np.isfinite(got).all()
             raw = M.field_lattice(xs, ys, zs, soften=False)
             if case == "clear":

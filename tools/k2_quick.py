@@ -32,3 +32,15 @@ for m, n_axis, h in CASES:
         dmax = float((out - base).abs().nan_to_num().max())
         print(json.dumps(dict(M=len(Q), L=len(seeds), h=h, cfg=cfg, ms=round(best, 3),
                               pairs_per_s="%.3e" % (c["pair_evals"] / (best * 1e-3)), maxdiff_vs_first=dmax)), flush=True)
+# small line sets (shipped example 3A: 18^3; a 6^3 probe): one line per warp spread over all SMs
+for n_axis in (18, 6, 3):
+    x, Q = synth.charges(7890, seed=1, box=0.5)
+    seeds, n_iter, dims, _ = synth.seeds(n_axis, 0.5, 0.1)
+    sd = torch.from_numpy(seeds).cuda(); ni = torch.from_numpy(n_iter.astype(np.int32)).cuda()
+    eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
+    for cfg in [dict(), dict(k2_threads=512)]:
+        eng.set_tuning(k2_threads=0, k2_cap=0, k2_sort=-1); eng.set_tuning(**cfg)
+        best = 1e30
+        for _ in range(3):
+            eng.topo_batch(sd, ni, 0.1, dims); torch.cuda.synchronize(); best = min(best, eng.last_kernel_ms())
+        print(json.dumps(dict(M=len(Q), L=len(seeds), cfg=cfg, ms=round(best, 4))), flush=True)
