@@ -563,9 +563,11 @@ static int launch_topo_warpwide(cpet_ctx* c, int n_lines, const float* d_seeds, 
         smem = hdr + all_bytes;
     } else {
         prm.resident = 0;
-        prm.tile_blocks = (tu.k2_tile_pairs > 0 ? tu.k2_tile_pairs : 2048) / 32;
+        // measured (tools/stream_exp.py, M = 100k): 512-pair tiles x 8 stages 2.20e12, 1024 x 6 2.36e12,
+        // 2048 x 3 2.45e12, 3072 x 2 2.47e12 -- every tile costs a CTA barrier and an FP64 fold
+        prm.tile_blocks = (tu.k2_tile_pairs > 0 ? tu.k2_tile_pairs : 3072) / 32;
         if (prm.tile_blocks < 1) prm.tile_blocks = 1;
-        prm.stages = tu.k2_stages > 0 ? tu.k2_stages : 3;
+        prm.stages = tu.k2_stages > 0 ? tu.k2_stages : 2;
         if (prm.stages > 8) prm.stages = 8;
         if (prm.stages < 2) prm.stages = 2;
         while (prm.tile_blocks > 1 &&

@@ -537,6 +537,37 @@ def test_topo_edge_cases(M, frame2a):
     assert np.all(z[:, 0] == 0.0) and np.all(np.isfinite(z[:, 1]))
 
 
+@pytest.mark.parametrize("m_charges", [1, 2, 63, 64, 65, 127, 129, 1000, 13500, 13700])
+def test_topo_ragged_sizes(M, m_charges):
+    """Charge counts around the 32-pair block padding and the shared-memory residency limit, line
+    counts around the warp / lines-per-warp boundaries, every result against the oracle; batches of
+    different composition give each line the same bits."""
+    x, Q = synth.charges(m_charges, seed=40 + m_charges % 7, box=0.5)
+    rng = np.random.default_rng(m_charges)
+    dims = np.array([0.5, 0.4, 0.5], np.float32)
+    reset_tuning(M)
+    M.set_charges(x, Q)
+    ref_rows = None
+    for L in (1, 3, 4, 5, 31, 33, 150, 2500):
+        seeds = (rng.uniform(-1, 1, (L, 3)) * dims * 0.98).astype(np.float32)
+        n_iter = rng.integers(0, 12, L)
+        want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
+        got, steps = M.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, want_steps=True)
+        ok = np.isfinite(want).all(axis=1) & (steps == wsteps)
+        assert (steps != wsteps).sum() <= max(1, L // 500)
+        if ok.any():
+            check_lines(got[ok], steps[ok], want[ok], wsteps[ok], 0.1, curv_tol_field_limited(0.1))
+        if L == 2500:
+            ref_rows = (seeds, n_iter, got)
+    # the first 100 lines alone, and with 4 / 2 / 1 lines per warp: same bits as inside the big batch
+    seeds, n_iter, got = ref_rows
+    for cfg in (dict(), dict(k2_cap=4), dict(k2_cap=2), dict(k2_cap=1, k2_threads=96)):
+        M.set_tuning(**cfg)
+        sub = M.topo_batch(seeds[:100], n_iter[:100], step_size=0.1, dimensions=dims)
+        np.testing.assert_array_equal(sub, got[:100])
+        reset_tuning(M)
+
+
 def test_topo_full_size_3A_properties(M, frame2a):
     """Configuration 3A at the size BASELINE.json names (47^3 = 103,823 seeds, h = 0.1, 17 max
     steps): invariants + order independence + oracle parity on a sample."""
