@@ -41,13 +41,22 @@ FLOPS_PER_PAIR = 20.0            # BASELINE.json north_star: "counted at 20 flop
 ESP_FLOPS_PER_PAIR = 11.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.5: 148 SM x 128 lanes x 2 x 1.965 GHz
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the
-# `ncu --set full` capture summarised in profiles/round1_k2w_ncu.md (same inputs as the bench)
-NCU_TRAFFIC = {
-    "topo3a": (2265344, "profiles/round1_k2w_ncu.md k2w_topo_kernel<0,4,4>: 2.27 MB read + 0 B written back "
-                        "during the kernel (seeds 12 B + n_iter 4 B + queue order 4 B per line; the 8 B/line "
-                        "output is still in L2 when the kernel ends)"),
-}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from one
+# `ncu --set full` capture of that kernel on the same synthetic inputs (tools/prof_workloads.py;
+# summaries in profiles/round1_k2w_ncu.md and profiles/round1_ncu_summary.md)
+def _load_traffic():
+    path = os.path.join(ROOT, "profiles", "round1_traffic.json")
+    try:
+        with open(path) as fh:
+            data = json.load(fh)
+    except (OSError, ValueError):
+        return {}
+    return {k: (int(v["traffic"]), f"profiles/round1_traffic.json: {v['kernel']}, {v['dram_read']} B read + "
+                                   f"{v['dram_write']} B written back to DRAM during the launch ({v['source']})")
+            for k, v in data.items()}
+
+
+NCU_TRAFFIC = _load_traffic()
 
 WORKLOADS = {
     # name: (kind, description, params)

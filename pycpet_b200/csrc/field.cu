@@ -86,7 +86,7 @@ struct K1Params {
                       // 4 (N,3) f32 p + h E/|E|  (propagate_topo, C:489-503)
     float step;
     void* out;
-    double* partial;  // [splits][n_points][3] when gridDim.y > 1
+    double* partial;  // [splits][n_points][3 (field) or 1 (ESP)] when gridDim.y > 1
 };
 
 __device__ __forceinline__ void store_result(int out_kind, float step, void* out, int pt, float x,
@@ -208,21 +208,25 @@ __global__ void __launch_bounds__(256) k1_grid_kernel(const K1Params prm) {
             store_result(prm.out_kind, prm.step, prm.out, pt[p], px[p], py[p], pz[p], acc[p][0],
                          acc[p][1], acc[p][2]);
         } else {
-            double* o = prm.partial + ((size_t)blockIdx.y * prm.n_points + pt[p]) * 3;
-            o[0] = acc[p][0]; o[1] = acc[p][1]; o[2] = acc[p][2];
+            // [split][point][1 (ESP) or 3 (field)] doubles
+            constexpr int NC = (MODE == MODE_ESP) ? 1 : 3;
+            double* o = prm.partial + ((size_t)blockIdx.y * prm.n_points + pt[p]) * NC;
+            o[0] = acc[p][0];
+            if (MODE != MODE_ESP) { o[1] = acc[p][1]; o[2] = acc[p][2]; }
         }
     }
 }
 
-__global__ void k1_finalize_kernel(const double* __restrict__ partial, int splits, int n_points,
+__global__ void k1_finalize_kernel(const double* __restrict__ partial, int splits, int n_points, int ncomp,
                                    const float* __restrict__ x0, int out_kind, float step,
                                    void* out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_points) return;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for (int s = 0; s < splits; ++s) {
-        const double* p = partial + ((size_t)s * n_points + i) * 3;
-        s0 += p[0]; s1 += p[1]; s2 += p[2];
+        const double* p = partial + ((size_t)s * n_points + i) * ncomp;
+        s0 += p[0];
+        if (ncomp == 3) { s1 += p[1]; s2 += p[2]; }
     }
     store_result(out_kind, step, out, i, x0[3 * (size_t)i], x0[3 * (size_t)i + 1], x0[3 * (size_t)i + 2],
                  s0, s1, s2);
@@ -368,14 +372,16 @@ __global__ void __launch_bounds__(256) k1_lattice_kernel(const K1LatParams prm) 
         if (gridDim.y == 1) {
             store_result(prm.out_kind, prm.step, prm.out, pt, x, y, z[p], acc[p][0], acc[p][1], acc[p][2]);
         } else {
-            double* o = prm.partial + ((size_t)blockIdx.y * prm.n_points + pt) * 3;
-            o[0] = acc[p][0]; o[1] = acc[p][1]; o[2] = acc[p][2];
+            constexpr int NC = (MODE == MODE_ESP) ? 1 : 3;
+            double* o = prm.partial + ((size_t)blockIdx.y * prm.n_points + pt) * NC;
+            o[0] = acc[p][0];
+            if (MODE != MODE_ESP) { o[1] = acc[p][1]; o[2] = acc[p][2]; }
         }
     }
 }
 
 // finalize for the lattice path: coordinates come from the axis arrays
-__global__ void k1_lattice_finalize_kernel(const double* __restrict__ partial, int splits, int n_points,
+__global__ void k1_lattice_finalize_kernel(const double* __restrict__ partial, int splits, int n_points, int ncomp,
                                            const float* __restrict__ xs, const float* __restrict__ ys,
                                            const float* __restrict__ zs, int ny, int nz, int out_kind,
                                            float step, void* out) {
@@ -383,8 +389,9 @@ __global__ void k1_lattice_finalize_kernel(const double* __restrict__ partial, i
     if (i >= n_points) return;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for (int s = 0; s < splits; ++s) {
-        const double* p = partial + ((size_t)s * n_points + i) * 3;
-        s0 += p[0]; s1 += p[1]; s2 += p[2];
+        const double* p = partial + ((size_t)s * n_points + i) * ncomp;
+        s0 += p[0];
+        if (ncomp == 3) { s1 += p[1]; s2 += p[2]; }
     }
     const int iz = i % nz;
     const int col = i / nz;
@@ -443,7 +450,8 @@ int launch_field_lattice(cpet_ctx* c, int mode, int nx, int ny, int nz, const fl
             if (ineff <= 1.02) break;
         }
     }
-    while (splits > 1 && (size_t)splits * (size_t)n_points * 24u > ((size_t)1 << 30)) --splits;
+    const int ncomp = (mode == MODE_ESP) ? 1 : 3;      // FP64 partial sums per point and split
+    while (splits > 1 && (size_t)splits * (size_t)n_points * 8u * ncomp > ((size_t)1 << 30)) --splits;
     int pps = (c->n_pairs + splits - 1) / splits;
     pps = ((pps + 7) / 8) * 8;
     if (pps < 8) pps = 8;
@@ -474,7 +482,7 @@ int launch_field_lattice(cpet_ctx* c, int mode, int nx, int ny, int nz, const fl
     prm.partial = nullptr;
     prm.soft_flag = nullptr;
     if (splits > 1) {
-        if (int rc = c->work0.reserve(sizeof(double) * 3 * (size_t)splits * (size_t)n_points)) return rc;
+        if (int rc = c->work0.reserve(sizeof(double) * ncomp * (size_t)splits * (size_t)n_points)) return rc;
         prm.partial = c->work0.as<double>();
     }
     int launches = 0;
@@ -517,7 +525,7 @@ int launch_field_lattice(cpet_ctx* c, int mode, int nx, int ny, int nz, const fl
     c->last_path = 1;
     if (splits > 1) {
         k1_lattice_finalize_kernel<<<(n_points + 255) / 256, 256, 0, c->stream>>>(
-            prm.partial, splits, n_points, d_xs, d_ys, d_zs, ny, nz, out_kind, 0.f, d_out);
+            prm.partial, splits, n_points, ncomp, d_xs, d_ys, d_zs, ny, nz, out_kind, 0.f, d_out);
         CPET_CUDA_TRY(cudaGetLastError());
         launches += 1;
     }
@@ -681,8 +689,9 @@ int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, in
             }
         }
     }
-    // FP64 partials cost 24 B per point per split: keep that scratch under 1 GiB
-    while (splits > 1 && (size_t)splits * (size_t)n_points * 24u > ((size_t)1 << 30)) --splits;
+    // FP64 partials cost 24 B (ESP: 8 B) per point per split: keep that scratch under 1 GiB
+    const int ncomp = (mode == MODE_ESP) ? 1 : 3;
+    while (splits > 1 && (size_t)splits * (size_t)n_points * 8u * ncomp > ((size_t)1 << 30)) --splits;
     const int min_pairs_per_split = 64;
     int max_splits = c->n_pairs / min_pairs_per_split;
     if (max_splits < 1) max_splits = 1;
@@ -720,7 +729,7 @@ int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, in
     prm.out = d_out;
     prm.partial = nullptr;
     if (splits > 1) {
-        if (int rc = c->work0.reserve(sizeof(double) * 3 * (size_t)splits * (size_t)n_points)) return rc;
+        if (int rc = c->work0.reserve(sizeof(double) * ncomp * (size_t)splits * (size_t)n_points)) return rc;
         prm.partial = c->work0.as<double>();
     }
 
@@ -735,7 +744,7 @@ int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, in
     c->last_path = 0;
     if (splits > 1) {
         k1_finalize_kernel<<<(n_points + 255) / 256, 256, 0, c->stream>>>(
-            prm.partial, splits, n_points, d_x0, out_kind, step, d_out);
+            prm.partial, splits, n_points, ncomp, d_x0, out_kind, step, d_out);
         CPET_CUDA_TRY(cudaGetLastError());
         c->last_counters[0] = 2;
     }
