@@ -322,7 +322,21 @@ int cpet_esp_grid(cpet_ctx* c, int n_points, const float* x0, unsigned flags, vo
     if (int rc = c->in0.reserve(sizeof(float) * 3 * n)) return rc;
     if (int rc = c->out0.reserve(out_bytes)) return rc;
     CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, x0, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
-    if (int rc = cpet_esp_grid_dev(c, n_points, c->in0.as<float>(), flags, c->out0.p)) return rc;
+    // box meshes (UC:450-475 hands over mesh.reshape(-1,3)) get the lattice kernel, as in cpet_field_grid
+    int is_lat = 0, nx = 0, ny = 0, nz = 0;
+    const float* d_axes = nullptr;
+    const bool try_lattice = c->tune.k1_lattice > 0 || (c->tune.k1_lattice < 0 && c->tune.k1_lanes == 0);
+    if (try_lattice) {
+        if (int rc = detect_lattice(c, n_points, c->in0.as<float>(), &is_lat, &nx, &ny, &nz, &d_axes)) return rc;
+    }
+    if (is_lat) {
+        CPET_REQUIRE((flags & ~CPET_OUT_CONCAT) == 0, CPET_ERR_INVALID, "unknown flag bits 0x%x", flags);
+        if (int rc = launch_field_lattice(c, MODE_ESP, nx, ny, nz, d_axes, d_axes + nx, d_axes + nx + ny,
+                                          (flags & CPET_OUT_CONCAT) ? 3 : 2, c->out0.p))
+            return rc;
+    } else {
+        if (int rc = cpet_esp_grid_dev(c, n_points, c->in0.as<float>(), flags, c->out0.p)) return rc;
+    }
     CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
     return CPET_OK;
