@@ -200,12 +200,22 @@ def order_stats_sharded(radix_hist, ranks):
 def frames_sharded(compute_frame, n_frames):
     """MD-frame batch: this rank runs compute_frame(f) for f = rank, rank+size, ...; the per-frame
     results (equal-shaped arrays/tensors) are gathered and returned stacked in frame order."""
+    return frames_batch_sharded(lambda ids: [compute_frame(f) for f in ids], n_frames)
+
+
+def frames_batch_sharded(compute_batch, n_frames):
+    """Same, with one call per rank: compute_batch(ids) gets this rank's frame ids (rank, rank+size,
+    ...) and returns one equal-shaped result per id (a list, or an array/tensor with leading
+    dimension len(ids)) -- the shape of Math_ops.topo_hist_frames, which overlaps the copies and
+    kernels of neighbouring frames.  Results come back stacked in frame order on every rank."""
     import torch
 
     rank, size = world()
     mine = frames_for_rank(n_frames, rank, size)
-    res = [compute_frame(f) for f in mine]
-    res = [r if torch.is_tensor(r) else torch.as_tensor(np.ascontiguousarray(r)) for r in res]
+    got = compute_batch(mine) if len(mine) else []
+    res = [r if torch.is_tensor(r) else torch.as_tensor(np.ascontiguousarray(r)) for r in got]
+    if len(res) != len(mine):
+        raise ValueError(f"compute_batch returned {len(res)} results for {len(mine)} frames")
     if size == 1:
         return torch.stack(res) if res else torch.zeros(0)
     shape = tuple(res[0].shape) if res else None

@@ -58,6 +58,18 @@ def main():
         rows = eng.topo_batch(torch.from_numpy(seeds[:4096]).cuda(), n_iter[:4096], 0.1, dims)
         return eng.hist2d(rows, np.linspace(0, 1.8, 51), np.linspace(0, 5, 51)).clone()
     frames = sharding.frames_sharded(frame, 6)
+    # the same frames through the MD-frame batch call (host C ABI, one call per rank) -> gather
+    def frame_charges(f):
+        rng = np.random.default_rng(100 + f)
+        xf = (x + rng.normal(0, 0.3, x.shape)).astype(np.float32)
+        xf[np.all(np.abs(xf) < 0.55, axis=1)] *= 3.0
+        return xf, Q
+    from pycpet_b200 import Math_ops
+    m = Math_ops(device=local)
+    batch = sharding.frames_batch_sharded(
+        lambda ids: m.topo_hist_frames([frame_charges(f) for f in ids], seeds[:4096], n_iter[:4096],
+                                       np.linspace(0, 1.8, 51), np.linspace(0, 5, 51), step_size=0.1,
+                                       dimensions=dims)[1], 6)
     torch.cuda.synchronize()
 
     ok = True
@@ -74,6 +86,7 @@ def main():
                                                          float(t1[:, 1].min()), float(t1[:, 1].max())),
             "hist all_reduce": torch.equal(counts.to(c1.device), c1) and int(counts.sum()) == len(seeds),
             "frames gather": torch.equal(frames.to(fr1.device).to(fr1.dtype), fr1),
+            "frames batch call + gather": torch.equal(batch.to(fr1.device).to(fr1.dtype).reshape(fr1.shape), fr1),
         }
         for k, v in checks.items():
             print(f"[nccl_check world={world}] {k}: {'OK' if v else 'MISMATCH'}")

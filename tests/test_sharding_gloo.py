@@ -59,13 +59,16 @@ def _worker(rank, size, port, tmp):
         lambda v, a, b: ohist.hist2d_counts(v[:, 0], v[:, 1], 7, 5, (a[0], a[-1]), (b[0], b[-1])),
         ref_topo[ids], de, ce).numpy()
     frames = sharding.frames_sharded(lambda f: np.full((2, 3), float(f)), 5).numpy()
+    # one call per rank over its frame ids (the shape of Math_ops.topo_hist_frames): int64 counts
+    batch = sharding.frames_batch_sharded(
+        lambda ids: np.stack([np.full((3, 2), 10 * f, dtype=np.int64) for f in ids]), 7).numpy()
     # exact global order statistics of values spread over the ranks (radix select + all-reduce)
     mine32 = ref_topo[ids][:, 1].astype(np.float32)
     n_all = len(ref_topo)
     stats = sharding.order_stats_sharded(lambda pre, bits: np_radix_hist(mine32, pre, bits),
                                          [0, n_all // 4, n_all // 2, (3 * n_all) // 4, n_all - 1])
     np.savez(os.path.join(tmp, f"r{rank}.npz"), field=full_field, topo=full_topo, counts=counts,
-             frames=frames, ranges=np.array([lo_d, hi_d, lo_c, hi_c]), stats=stats)
+             frames=frames, batch=batch, ranges=np.array([lo_d, hi_d, lo_c, hi_c]), stats=stats)
     dist.destroy_process_group()
 
 
@@ -90,6 +93,8 @@ def test_world_size_2_gloo(tmp_path):
         np.testing.assert_array_equal(z["counts"], expect)
         assert z["counts"].sum() == len(topo)
         np.testing.assert_array_equal(z["frames"][:, 0, 0], np.arange(5.0))
+        assert z["batch"].dtype == np.int64 and z["batch"].shape == (7, 3, 2)
+        np.testing.assert_array_equal(z["batch"][:, 2, 1], 10 * np.arange(7))
         srt = np.sort(topo[:, 1].astype(np.float32))
         n_all = len(srt)
         np.testing.assert_array_equal(z["stats"], srt[[0, n_all // 4, n_all // 2, (3 * n_all) // 4, n_all - 1]])
