@@ -135,6 +135,27 @@ static int resolve_topo_counters(cpet_ctx* c) {
     return CPET_OK;
 }
 
+// ---- MD-frame batch helpers (cpet_topo_hist_frames) ------------------------------------------
+// Two child contexts (own streams, own staging buffers) take the frames alternately: everything a
+// frame needs is enqueued on its child's stream -- H2D of its charges (and n_iter), pack, queue sort,
+// integrator, histogram, D2H of its counts (and rows) -- so the copies of frame f+1 / f-1 overlap
+// the kernels of frame f, and the CTAs of frame f+1 start on each SM as soon as frame f leaves it.
+__global__ void add_evals_kernel(const unsigned long long* __restrict__ evals, int n_charges,
+                                 unsigned long long* __restrict__ totals) {
+    totals[0] += *evals;
+    totals[1] += *evals * (unsigned long long)n_charges;
+}
+
+static int frames_child(cpet_ctx* c, int i, cpet_ctx** out) {
+    if (!c->pipe[i]) {
+        if (int rc = make_ctx(c->device, nullptr, false, &c->pipe[i])) return rc;
+    }
+    c->pipe[i]->tune = c->tune;
+    c->pipe[i]->tune.timing = 0;
+    *out = c->pipe[i];
+    return CPET_OK;
+}
+
 }  // namespace cpet
 
 using namespace cpet;
@@ -163,7 +184,7 @@ int cpet_destroy(cpet_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->charges.release(); c->charge_blocks.release(); c->raw_x.release(); c->raw_q.release();
     c->in0.release(); c->in1.release(); c->out0.release(); c->out1.release();
-    c->work0.release(); c->work1.release(); c->work2.release(); c->counters.release(); c->flags.release();
+    c->work0.release(); c->work1.release(); c->work2.release(); c->counters.release(); c->flags.release(); c->totals.release();
     for (int i = 0; i < cpet_ctx::kTimerRing; ++i) {
         if (c->ev0[i]) cudaEventDestroy(c->ev0[i]);
         if (c->ev1[i]) cudaEventDestroy(c->ev1[i]);
@@ -559,26 +580,6 @@ int cpet_topo_hist(cpet_ctx* c, int n_lines, const float* seeds, const int32_t* 
 }
 
 // ---------------------------------------------------------------- MD-frame batch -----------
-// Two child contexts (own streams, own staging buffers) take the frames alternately: everything a
-// frame needs is enqueued on its child's stream -- H2D of its charges (and n_iter), pack, queue sort,
-// integrator, histogram, D2H of its counts (and rows) -- so the copies of frame f+1 / f-1 overlap
-// the kernels of frame f, and the CTAs of frame f+1 start on each SM as soon as frame f leaves it.
-__global__ void add_evals_kernel(const unsigned long long* __restrict__ evals, int n_charges,
-                                 unsigned long long* __restrict__ totals) {
-    totals[0] += *evals;
-    totals[1] += *evals * (unsigned long long)n_charges;
-}
-
-static int frames_child(cpet_ctx* c, int i, cpet_ctx** out) {
-    if (!c->pipe[i]) {
-        if (int rc = make_ctx(c->device, nullptr, false, &c->pipe[i])) return rc;
-    }
-    c->pipe[i]->tune = c->tune;
-    c->pipe[i]->tune.timing = 0;
-    *out = c->pipe[i];
-    return CPET_OK;
-}
-
 int cpet_topo_hist_frames(cpet_ctx* c, int n_frames, const int* n_charges, const float* const* x,
                           const float* const* Q, int n_lines, const float* seeds, const int32_t* n_iter,
                           int64_t n_iter_frame_stride, float step_size, const float dims[3], unsigned flags,
@@ -612,8 +613,8 @@ int cpet_topo_hist_frames(cpet_ctx* c, int n_frames, const int* n_charges, const
         if (int rc = k->in1.reserve(sizeof(int32_t) * n)) return rc;
         if (int rc = k->out0.reserve(sizeof(float) * 2 * n)) return rc;
         if (int rc = k->work0.reserve(cbytes)) return rc;
-        if (int rc = k->flags.reserve(64)) return rc;
-        CPET_CUDA_TRY(cudaMemsetAsync(k->flags.p, 0, 64, k->stream));
+        if (int rc = k->totals.reserve(64)) return rc;
+        CPET_CUDA_TRY(cudaMemsetAsync(k->totals.p, 0, 64, k->stream));
         if (n_lines > 0) {
             CPET_CUDA_TRY(cudaMemcpyAsync(k->in0.p, seeds, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, k->stream));
             if (n_iter_frame_stride == 0)
@@ -637,7 +638,7 @@ int cpet_topo_hist_frames(cpet_ctx* c, int n_frames, const int* n_charges, const
             launches += k->last_counters[0];
             add_evals_kernel<<<1, 1, 0, k->stream>>>(
                 reinterpret_cast<const unsigned long long*>(k->counters.as<unsigned char>() + 8), k->n_charges,
-                k->flags.as<unsigned long long>());
+                k->totals.as<unsigned long long>());
             CPET_CUDA_TRY(cudaGetLastError());
         }
         if (int rc = launch_hist2d(k, 1, n_lines, k->out0.p, false, nd, kd, nc, kc, k->work0.as<unsigned long long>()))
@@ -650,7 +651,7 @@ int cpet_topo_hist_frames(cpet_ctx* c, int n_frames, const int* n_charges, const
     }
     unsigned long long tot[2][2] = {{0, 0}, {0, 0}};
     for (int i = 0; i < n_children; ++i) {
-        CPET_CUDA_TRY(cudaMemcpyAsync(tot[i], ch[i]->flags.p, sizeof(tot[i]), cudaMemcpyDeviceToHost, ch[i]->stream));
+        CPET_CUDA_TRY(cudaMemcpyAsync(tot[i], ch[i]->totals.p, sizeof(tot[i]), cudaMemcpyDeviceToHost, ch[i]->stream));
         CPET_CUDA_TRY(cudaStreamSynchronize(ch[i]->stream));
     }
     c->last_counters[0] = launches;

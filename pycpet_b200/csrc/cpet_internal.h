@@ -68,7 +68,7 @@ struct cpet_ctx {
     cpet::DevBuf charge_blocks;      // ChargeBlock[ceil(n_pairs / 32)], zero-charge padded
     cpet::DevBuf raw_x, raw_q;       // staging for host uploads
     // scratch
-    cpet::DevBuf in0, in1, out0, out1, work0, work1, work2, counters, flags;
+    cpet::DevBuf in0, in1, out0, out1, work0, work1, work2, counters, flags, totals;
     cpet::Tuning tune;
     int64_t last_counters[3] = {0, 0, 0};
     double last_kernel_ms = 0.0;
