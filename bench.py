@@ -400,7 +400,9 @@ def run_gpu(args, rank, world, local_rank):
                         "Math_ops.field_grid / esp_grid -> cpet_field_grid / cpet_esp_grid, one call per step, "
                         "pinned host buffers")},
         "gpu_launches": int(launches["n"]),
-        "roofline": {"bound": "fp32-non-tensor", "kernel": "k2w_topo_kernel" if kind == "topo" else "k1_grid_kernel",
+        "roofline": {"bound": "fp32-non-tensor", "kernel": ("k2w_topo_kernel" if kind == "topo" else
+                                ("k1_lattice_kernel" if kind == "field" and len(inp["points"]) >= 4096
+                                 else "k1_grid_kernel")),
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_source": "measured live: register-resident FMA loop (cpet_fp32_peak_probe, "
                                     f"FFMA2 {peak_ffma2:.1f} / FFMA {peak_ffma:.1f} TFLOP/s); "

@@ -25,7 +25,8 @@ def last_json(name):
 single = [("topo3a", "bench_topo3a_1gpu.log"), ("md1m", "bench_md1m.log"), ("topo_fine", "bench_topo_fine.log"),
           ("volume", "bench_volume.log"), ("esp101", "bench_esp101.log"), ("volume2a", "bench_volume2a.log")]
 multi = [("topo3a", 2, "bench_topo3a_2gpu.log"), ("topo3a", 4, "bench_topo3a_4gpu.log"),
-         ("topo3a", 8, "bench_topo3a_8gpu.log"), ("md1m", 8, "bench_md1m_8gpu.log")]
+         ("topo3a", 8, "bench_topo3a_8gpu.log"), ("md1m", 8, "bench_md1m_8gpu.log"),
+         ("volume", 8, "bench_volume_8gpu.log"), ("esp101", 8, "bench_esp101_8gpu.log")]
 md = [f"# {rnd} — bench.py lines (one B200 per rank)\n",
       "Each block is the single JSON line `python bench.py --workload <name>` printed on the GPU box (gpurun), reformatted.",
       "`value` = device-resident inputs, CUDA-event timed per step, L2 flushed between steps; `e2e` = host-pointer C-ABI with "
