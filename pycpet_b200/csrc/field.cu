@@ -645,22 +645,20 @@ int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, in
     threads = (threads / 32) * 32;
     if (threads < 32) threads = 32;
 
-    // lanes per point: enough threads to fill the machine even for tiny grids
+    // Lanes per point.  Measured (tools/k1_midsize.py, profiles/round1_k1_midsize.md): from ~2,000
+    // points up one thread per point with the charge range split over gridDim.y beats G lanes per
+    // point by 1.1-2.6x (G distinct addresses per LDS.128 and a butterfly per point cost more than
+    // the FP64 finalize); G = 32 only for tiny lists such as the 11^3 grid of example 2A.
     int G = tu.k1_lanes;
-    if (G <= 0) {
-        const long long full_wave = (long long)sms * 512;
-        if ((long long)n_points >= full_wave) G = 1;
-        else if ((long long)n_points * 8 >= full_wave) G = 8;
-        else G = 32;
-    }
+    if (G <= 0) G = (n_points >= 2048) ? 1 : 32;
     if (G != 1 && G != 8 && G != 32) G = (G < 8) ? 8 : 32;
     int P = tu.k1_points;
     if (G > 1) P = 1;
     else if (P <= 0) {
-        // measured (profiles/round1_sweep.md): E-field best at 4 points/thread, ESP (MUFU-bound) at 2
+        // points per thread: register blocking pays once there are enough points to fill the chip
         const long long n = n_points;
-        if (mode == MODE_ESP) P = (n >= (long long)sms * 2048) ? 2 : 1;
-        else P = (n >= (long long)sms * 4096) ? 4 : ((n >= (long long)sms * 2048) ? 2 : 1);
+        if (mode == MODE_ESP) P = (n >= 16384) ? 2 : 1;                 // MUFU-bound: 2 is enough
+        else P = (n >= (long long)sms * 1024) ? 4 : ((n >= 16384) ? 2 : 1);
     }
     if (P != 1 && P != 2 && P != 4) P = 2;
 
