@@ -106,6 +106,23 @@ def compute_topo_batch(seeds, n_iter, x, Q, step_size, dimensions, second_diff=F
                                  second_diff=second_diff, want_steps=want_steps)
 
 
+def compute_curv_and_dist(x_init, x_init_plus, x_init_plus_plus, x_0, x_0_plus, x_0_plus_plus):
+    """UC:541-562 -> [dist, curv_mean] from the first three and the last three points of ONE
+    streamline: kappa = |v' x v''| / |v'|^3 with v' = a1 - a0, v'' = a2 - 2 a1 + a0 (UC:500-521,
+    eps = 10e-6 replaces a zero denominator), mean of both ends, dist = |x_init - x_0|.
+    Six points of host arithmetic in the caller's dtype, exactly as the reference writes it; the
+    integrator applies the same two formulas per line on the device (topo_batch, second_diff=True
+    for this literal second-difference form)."""
+    def curv(v1, v2, eps=10e-6):
+        den = np.linalg.norm(v1, axis=0) ** 3
+        num = np.linalg.norm(np.cross(v1, v2), axis=0)
+        return num / eps if den == 0 else num / den
+
+    curv_init = curv(x_init_plus - x_init, x_init_plus_plus - 2 * x_init_plus + x_init)
+    curv_final = curv(x_0_plus - x_0, x_0_plus_plus - 2 * x_0_plus + x_0)
+    return [np.linalg.norm(x_init - x_0, axis=-1), (curv_init + curv_final) / 2]
+
+
 def distance_numpy(hist1, hist2):
     """UC:975-978: chi^2 distance between two flattened normalised histograms (device)."""
     H = np.stack([np.asarray(hist1, dtype=np.float64).ravel(), np.asarray(hist2, dtype=np.float64).ravel()])

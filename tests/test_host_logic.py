@@ -60,3 +60,24 @@ def test_plan_from_order_stats_reproduces_numpy_scipy():
             x64 = allv[:, col].astype(np.float64)
             assert calc._lerp(a25, b25, g25) == np.percentile(x64, 25)
             assert calc._lerp(a75, b75, g75) == np.percentile(x64, 75)
+
+
+def test_compute_curv_and_dist_known_answers():
+    """UC:541-562 mirror: curvature of a circle is 1/R, of a straight line 0; a zero first
+    difference takes the eps branch (UC:517-518); dist is the end-to-end distance."""
+    from pycpet_b200 import calculator as calc
+
+    R, h = 2.0, 0.01
+    def on_circle(t0):
+        t = t0 + np.arange(3) * (h / R)
+        return [np.array([R * np.cos(a), R * np.sin(a), 0.3]) for a in t]
+    a0, a1, a2 = on_circle(0.2)
+    b0, b1, b2 = on_circle(1.1)
+    dist, curv = calc.compute_curv_and_dist(a0, a1, a2, b0, b1, b2)
+    assert abs(curv - 1.0 / R) < 1e-4
+    assert abs(dist - np.linalg.norm(a0 - b0)) < 1e-15
+    p = np.array([0.1, -0.2, 0.3]); d = np.array([0.3, 0.4, 0.5])
+    dist, curv = calc.compute_curv_and_dist(p, p + d, p + 2 * d, p + 5 * d, p + 6 * d, p + 7 * d)
+    assert curv < 1e-12 and abs(dist - 5 * np.linalg.norm(d)) < 1e-12
+    dist, curv = calc.compute_curv_and_dist(p, p, p + d, p, p, p + d)      # v' = 0 -> num / eps = 0 / 1e-5
+    assert curv == 0.0 and dist == 0.0
