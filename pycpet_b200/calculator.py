@@ -89,6 +89,13 @@ def calculate_thread_c_shared(x_0, n_iter, x, Q, step_size, dimensions):
                                        dimensions=dimensions)
 
 
+def calculate_thread_c_shared_dipole(x_0, n_iter, x, mu, step_size, dimensions):
+    """UC:351-358 (marked in-development in the reference; used by CPET/utils/parallel.py:121):
+    one streamline in the field of point dipoles mu at x -> (2,) float32 [dist, curv]."""
+    return get_math().thread_operation_dipole(x_0=x_0, n_iter=n_iter, x=x, mu=mu, step_size=step_size,
+                                              dimensions=dimensions)
+
+
 def propagate_topo(x_0, x, Q, step_size, debug=False):
     """One normalised-field step p + h E(p)/|E(p)| on the device (the C propagate_topo,
     math_module.c:489-503; UC:35-54 is its Python twin).  x_0 (3,) or (N,3) -> same shape."""
