@@ -135,10 +135,14 @@ def run_topo_frames(options, files, outputpath=None, d_edges=None, c_edges=None,
                 batch = []
         if batch:
             emit(batch)
-    finally:
+    except BaseException:
         if pool is not None:
-            pool.close()
+            pool.terminate()        # a failed constructor or GPU call: do not parse the rest
             pool.join()
+        raise
+    if pool is not None:
+        pool.close()
+        pool.join()
     if want_counts:
         result["counts"] = (np.stack(result["counts"]) if result["counts"]
                             else np.zeros((0, len(d_edges) - 1, len(c_edges) - 1), np.int64))

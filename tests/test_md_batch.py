@@ -88,3 +88,22 @@ def test_worker_processes_keep_the_file_order():
     assert b["files"] == files and m.calls == [3, 3, 1]
     for ra, rb in zip(a["rows"], b["rows"]):
         np.testing.assert_array_equal(ra, rb)
+
+
+def failing_prepare(options, path):
+    if "3_" in path:
+        raise ValueError(f"cannot parse {path}")
+    return fake_prepare(options, path)
+
+
+def test_a_failing_constructor_surfaces_and_stops_the_batch(tmp_path):
+    import pytest
+
+    files = [f"/x/{k}_f.pdb" for k in range(6)]
+    for workers in (0, 2):
+        m = FakeMath()
+        with pytest.raises(ValueError, match="cannot parse"):
+            md_batch.run_topo_frames({}, files, outputpath=str(tmp_path / f"o{workers}"), workers=workers, chunk=2,
+                                     math=m, prepare=failing_prepare)
+        assert m.calls == [2]                       # frames 0,1 were done and written before the failure
+        assert sorted(os.listdir(tmp_path / f"o{workers}")) == ["0_f.top", "1_f.top"]
