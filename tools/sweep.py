@@ -69,7 +69,7 @@ def main():
             ni = torch.from_numpy(n_iter.astype(np.int32)).cuda()
             eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
             for cap, thr, srt in itertools.product((0, 1, 2, 4), (256, 384, 512), (1, 0)):
-                if srt == 0 and (cap != 0 or thr != 512):
+                if srt == 0 and (cap != 4 or thr != 512):     # unsorted queue: one reference point per case
                     continue
                 eng.set_tuning(k2_cap=cap, k2_threads=thr, k2_sort=(-1 if cap == 0 else srt))
                 ms = timed(eng, lambda: eng.topo_batch(sd, ni, h, dims), reps=2)
