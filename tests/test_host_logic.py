@@ -81,3 +81,22 @@ def test_compute_curv_and_dist_known_answers():
     assert curv < 1e-12 and abs(dist - 5 * np.linalg.norm(d)) < 1e-12
     dist, curv = calc.compute_curv_and_dist(p, p, p + d, p, p, p + d)      # v' = 0 -> num / eps = 0 / 1e-5
     assert curv == 0.0 and dist == 0.0
+
+
+def test_topo_hist_frames_argument_checks_need_no_device():
+    """Shape errors of the MD-frame batch call are raised by the Python mirror before anything
+    touches the GPU (the reference's ndpointer argtypes reject bad shapes the same way)."""
+    import pytest
+
+    from pycpet_b200 import Math_ops
+
+    m = Math_ops()
+    seeds = np.zeros((5, 3), np.float32)
+    frames = [(np.zeros((4, 3), np.float32), np.zeros(4, np.float32))] * 3
+    e = np.linspace(0, 1, 4)
+    with pytest.raises(ValueError, match="n_iter"):
+        m.topo_hist_frames(frames, seeds, np.ones(4, np.int32), e, e)
+    with pytest.raises(ValueError, match="n_iter"):
+        m.topo_hist_frames(frames, seeds, np.ones((2, 5), np.int32), e, e)
+    with pytest.raises(ValueError, match="rows but Q"):
+        m.topo_hist_frames([(np.zeros((4, 3), np.float32), np.zeros(3, np.float32))], seeds, np.ones(5, np.int32), e, e)
