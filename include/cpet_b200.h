@@ -105,8 +105,13 @@ int cpet_esp_grid_dev(cpet_ctx *ctx, int n_points, const float *d_x0, unsigned f
  * with k fastest -- exactly the mesh initialize_box_points_uniform builds (UC:218-233:
  * linspace per axis, meshgrid(indexing="ij"), reshape(-1,3)) and compute_field_on_grid /
  * compute_ESP_on_grid receive.  dx, dy and dx^2+dy^2 are shared along z, which removes a quarter of
- * the FP32 instructions per pair; results are bit-identical to cpet_field_grid / cpet_esp_grid on
- * the expanded point list.  Output layouts and flags as above (N = nx*ny*nz rows). */
+ * the FP32 instructions per pair; with the same charge-range split ("k1_splits") results are
+ * bit-identical to the general kernel on the expanded point list, otherwise they differ in the
+ * order of the FP64 partial sums only.  The host forms cpet_field_grid / cpet_esp_grid recognise
+ * such meshes (>= 4096 points) by themselves and take this kernel; with CPET_FIELD_SOFTEN and
+ * >= 2e9 pair-evaluations a device scan first proves that max(r^2, 1e-6) cannot act, and the
+ * unsoftened instantiation then serves the call with the same bits ("k1_softscan").
+ * Output layouts and flags as above (N = nx*ny*nz rows). */
 int cpet_field_lattice(cpet_ctx *ctx, int nx, int ny, int nz, const float *xs, const float *ys,
                        const float *zs, unsigned flags, float *out);
 int cpet_field_lattice_dev(cpet_ctx *ctx, int nx, int ny, int nz, const float *d_xs,
