@@ -605,55 +605,78 @@ int cpet_topo_hist_frames(cpet_ctx* c, int n_frames, const int* n_charges, const
     const int n_children = n_frames > 1 ? 2 : 1;
     cpet_ctx* ch[2] = {nullptr, nullptr};
     const double* dd[2]; const double* dc[2];
-    for (int i = 0; i < n_children; ++i) {
-        if (int rc = frames_child(c, i, &ch[i])) return rc;
-        cpet_ctx* k = ch[i];
-        if (int rc = upload_edges(k, nd, d_edges, nc, c_edges, &dd[i], &dc[i])) return rc;
-        if (int rc = k->in0.reserve(sizeof(float) * 3 * n)) return rc;
-        if (int rc = k->in1.reserve(sizeof(int32_t) * n)) return rc;
-        if (int rc = k->out0.reserve(sizeof(float) * 2 * n)) return rc;
-        if (int rc = k->work0.reserve(cbytes)) return rc;
-        if (int rc = k->totals.reserve(64)) return rc;
-        CPET_CUDA_TRY(cudaMemsetAsync(k->totals.p, 0, 64, k->stream));
-        if (n_lines > 0) {
-            CPET_CUDA_TRY(cudaMemcpyAsync(k->in0.p, seeds, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, k->stream));
-            if (n_iter_frame_stride == 0)
-                CPET_CUDA_TRY(cudaMemcpyAsync(k->in1.p, n_iter, sizeof(int32_t) * n, cudaMemcpyHostToDevice, k->stream));
+    auto setup = [&]() -> int {
+        for (int i = 0; i < n_children; ++i) {
+            if (int rc = frames_child(c, i, &ch[i])) return rc;
+            cpet_ctx* k = ch[i];
+            if (int rc = upload_edges(k, nd, d_edges, nc, c_edges, &dd[i], &dc[i])) return rc;
+            if (int rc = k->in0.reserve(sizeof(float) * 3 * n)) return rc;
+            if (int rc = k->in1.reserve(sizeof(int32_t) * n)) return rc;
+            if (int rc = k->out0.reserve(sizeof(float) * 2 * n)) return rc;
+            if (int rc = k->work0.reserve(cbytes)) return rc;
+            if (int rc = k->totals.reserve(64)) return rc;
+            CPET_CUDA_TRY(cudaMemsetAsync(k->totals.p, 0, 64, k->stream));
+            if (n_lines > 0) {
+                CPET_CUDA_TRY(cudaMemcpyAsync(k->in0.p, seeds, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, k->stream));
+                if (n_iter_frame_stride == 0)
+                    CPET_CUDA_TRY(cudaMemcpyAsync(k->in1.p, n_iter, sizeof(int32_t) * n, cudaMemcpyHostToDevice, k->stream));
+            }
         }
+        return CPET_OK;
+    };
+    if (int rc = setup()) {
+        for (int i = 0; i < n_children; ++i)
+            if (ch[i]) cudaStreamSynchronize(ch[i]->stream);     // seeds / edges copies in flight
+        return rc;
     }
     int64_t launches = 0;
-    for (int f = 0; f < n_frames; ++f) {
-        cpet_ctx* k = ch[f % n_children];
-        const double* kd = dd[f % n_children];
-        const double* kc = dc[f % n_children];
-        if (int rc = cpet_set_charges(k, n_charges[f], x[f], Q[f])) return rc;
-        launches += 1;
-        if (n_lines > 0) {
-            if (n_iter_frame_stride != 0)
-                CPET_CUDA_TRY(cudaMemcpyAsync(k->in1.p, n_iter + (size_t)f * (size_t)n_iter_frame_stride,
-                                              sizeof(int32_t) * n, cudaMemcpyHostToDevice, k->stream));
-            if (int rc = launch_topo(k, n_lines, k->in0.as<float>(), k->in1.as<int32_t>(), step_size, dims, flags,
-                                     k->out0.as<float>(), nullptr))
+    // every frame's work is enqueued asynchronously; whatever happens, both streams are drained before
+    // this call returns, because the copies reference the caller's host buffers
+    auto enqueue = [&]() -> int {
+        for (int f = 0; f < n_frames; ++f) {
+            cpet_ctx* k = ch[f % n_children];
+            const double* kd = dd[f % n_children];
+            const double* kc = dc[f % n_children];
+            if (int rc = cpet_set_charges(k, n_charges[f], x[f], Q[f])) return rc;
+            launches += 1;
+            if (n_lines > 0) {
+                if (n_iter_frame_stride != 0)
+                    CPET_CUDA_TRY(cudaMemcpyAsync(k->in1.p, n_iter + (size_t)f * (size_t)n_iter_frame_stride,
+                                                  sizeof(int32_t) * n, cudaMemcpyHostToDevice, k->stream));
+                if (int rc = launch_topo(k, n_lines, k->in0.as<float>(), k->in1.as<int32_t>(), step_size, dims, flags,
+                                         k->out0.as<float>(), nullptr))
+                    return rc;
+                launches += k->last_counters[0];
+                add_evals_kernel<<<1, 1, 0, k->stream>>>(
+                    reinterpret_cast<const unsigned long long*>(k->counters.as<unsigned char>() + 8), k->n_charges,
+                    k->totals.as<unsigned long long>());
+                CPET_CUDA_TRY(cudaGetLastError());
+            }
+            if (int rc = launch_hist2d(k, 1, n_lines, k->out0.p, false, nd, kd, nc, kc, k->work0.as<unsigned long long>()))
                 return rc;
             launches += k->last_counters[0];
-            add_evals_kernel<<<1, 1, 0, k->stream>>>(
-                reinterpret_cast<const unsigned long long*>(k->counters.as<unsigned char>() + 8), k->n_charges,
-                k->totals.as<unsigned long long>());
-            CPET_CUDA_TRY(cudaGetLastError());
+            if (n_lines > 0 && out_rows)
+                CPET_CUDA_TRY(cudaMemcpyAsync(out_rows + (size_t)f * 2 * n, k->out0.p, sizeof(float) * 2 * n,
+                                              cudaMemcpyDeviceToHost, k->stream));
+            CPET_CUDA_TRY(cudaMemcpyAsync(counts + (size_t)f * nd * nc, k->work0.p, cbytes, cudaMemcpyDeviceToHost, k->stream));
         }
-        if (int rc = launch_hist2d(k, 1, n_lines, k->out0.p, false, nd, kd, nc, kc, k->work0.as<unsigned long long>()))
-            return rc;
-        launches += k->last_counters[0];
-        if (n_lines > 0 && out_rows)
-            CPET_CUDA_TRY(cudaMemcpyAsync(out_rows + (size_t)f * 2 * n, k->out0.p, sizeof(float) * 2 * n,
-                                          cudaMemcpyDeviceToHost, k->stream));
-        CPET_CUDA_TRY(cudaMemcpyAsync(counts + (size_t)f * nd * nc, k->work0.p, cbytes, cudaMemcpyDeviceToHost, k->stream));
-    }
+        return CPET_OK;
+    };
+    const int rc_enqueue = enqueue();
     unsigned long long tot[2][2] = {{0, 0}, {0, 0}};
+    int rc_sync = CPET_OK;
     for (int i = 0; i < n_children; ++i) {
-        CPET_CUDA_TRY(cudaMemcpyAsync(tot[i], ch[i]->totals.p, sizeof(tot[i]), cudaMemcpyDeviceToHost, ch[i]->stream));
-        CPET_CUDA_TRY(cudaStreamSynchronize(ch[i]->stream));
+        if (rc_enqueue == CPET_OK &&
+            cudaMemcpyAsync(tot[i], ch[i]->totals.p, sizeof(tot[i]), cudaMemcpyDeviceToHost, ch[i]->stream) != cudaSuccess)
+            rc_sync = CPET_ERR_CUDA;
+        const cudaError_t e = cudaStreamSynchronize(ch[i]->stream);
+        if (e != cudaSuccess && rc_enqueue == CPET_OK && rc_sync == CPET_OK) {
+            set_error(CPET_ERR_CUDA, "cpet_topo_hist_frames: stream %d failed: %s", i, cudaGetErrorString(e));
+            rc_sync = CPET_ERR_CUDA;
+        }
     }
+    if (rc_enqueue != CPET_OK) return rc_enqueue;
+    if (rc_sync != CPET_OK) return rc_sync;
     c->last_counters[0] = launches;
     c->last_counters[2] = (int64_t)(tot[0][0] + tot[1][0]);
     c->last_counters[1] = (int64_t)(tot[0][1] + tot[1][1]);
