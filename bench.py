@@ -31,12 +31,19 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun sets this for N > 1; do the same at N = 1 so that idle OpenMP workers of the host math
+# libraries do not spin next to the thread that enqueues the end-to-end arm (the CPU reference arm
+# uses forked worker processes, not OpenMP)
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+FRAME_POOL = 8                   # distinct MD frames cycled by the streamline workloads
+GATHER_WINDOW = 4                # per-frame histogram all-gathers allowed in flight (N > 1)
 FLOPS_PER_PAIR = 20.0            # BASELINE.json north_star: "counted at 20 flops/pair"
 ESP_FLOPS_PER_PAIR = 11.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.5: 148 SM x 128 lanes x 2 x 1.965 GHz
@@ -187,13 +194,23 @@ def run_gpu(args, rank, world, local_rank):
     kind, desc, prm = WORKLOADS[args.workload]
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    inp = make_inputs(kind, prm, frame_id=rank)
+    # Streamline workloads run a trajectory: POOL frames (base charge set + per-frame jitter),
+    # rank r integrates frame (r + s) mod POOL at step s -- a different frame on every GPU at every step, and
+    # the same mix of frames on every rank whatever N is.  Grid workloads: one frame per rank (equal work).
+    if kind == "topo":
+        pool = [make_inputs(kind, prm, frame_id=j) for j in range(FRAME_POOL)]
+        inp = pool[0]
+    else:
+        inp = make_inputs(kind, prm, frame_id=rank)
+        pool = [inp]
     de, ce = hist_edges(kind, prm)
 
     # ---- device-resident arm ---------------------------------------------------------------
     eng = Engine(local_rank)
     eng.set_tuning(timing=1)
-    dx, dq = torch.from_numpy(inp["x"]).to(dev), torch.from_numpy(inp["Q"]).to(dev)
+    dcharges = [(torch.from_numpy(f["x"]).to(dev), torch.from_numpy(f["Q"]).to(dev)) for f in pool]
+    pool_pairs = [0] * len(pool)        # pair-evaluations of every pool frame (probe pass, untimed)
+    seq = {"s": 0}                      # steps issued so far on this rank (warm-up included)
     if kind == "topo":
         dseeds, dnit = torch.from_numpy(inp["seeds"]).to(dev), torch.from_numpy(inp["n_iter"]).to(dev)
         dout = torch.empty((len(inp["seeds"]), 2), dtype=torch.float32, device=dev)
@@ -206,10 +223,10 @@ def run_gpu(args, rank, world, local_rank):
                 else torch.empty((n, 4), dtype=torch.float16, device=dev))
     pending = []        # in-flight NCCL gathers of per-frame histograms (world > 1)
 
-    def drain():
-        for h, _, _ in pending:
-            h.wait()
-        pending.clear()
+    def drain(keep=0):
+        """Wait for the oldest histogram gathers until at most `keep` are in flight."""
+        while len(pending) > keep:
+            pending.pop(0)[0].wait()
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     launches = {"n": 0}
     kern_ms = []
@@ -218,13 +235,16 @@ def run_gpu(args, rank, world, local_rank):
     def step_device(probe=False):
         """One step, fully asynchronous (no host synchronisation inside the timed region).
         probe=True (warm-up only) additionally reads the work counters back."""
-        eng.set_charges(dx, dq)                                          # pack kernel
+        j = (rank + seq["s"]) % len(pool)
+        seq["s"] += 1
+        eng.set_charges(*dcharges[j])                                    # pack kernel
         n_launch = 1
         if kind == "topo":
             eng.topo_batch(dseeds, dnit, inp["h"], inp["dims"], out=dout)
             if probe:
                 c = eng.last_counters()
-                work["pairs"], work["units"], work["k_launch"] = c["pair_evals"], len(inp["seeds"]), c["launches"]
+                pool_pairs[j] = c["pair_evals"]
+                work["units"], work["k_launch"] = len(inp["seeds"]), c["launches"]
             eng.hist2d(dout, de, ce, out=dcounts)
             n_launch += work["k_launch"] + 1
             if world > 1:
@@ -243,13 +263,15 @@ def run_gpu(args, rank, world, local_rank):
                 eng.field_grid(dpts, soften=True, concat=True, out=dout)
             if probe:
                 c = eng.last_counters()
-                work["pairs"], work["units"], work["k_launch"] = c["pair_evals"], len(inp["points"]), c["launches"]
+                pool_pairs[j] = c["pair_evals"]
+                work["units"], work["k_launch"] = len(inp["points"]), c["launches"]
             n_launch += work["k_launch"]
         else:
             eng.esp_grid(dpts, concat_half=True, out=dout)
             if probe:
                 c = eng.last_counters()
-                work["pairs"], work["units"], work["k_launch"] = c["pair_evals"], len(inp["points"]), c["launches"]
+                pool_pairs[j] = c["pair_evals"]
+                work["units"], work["k_launch"] = len(inp["points"]), c["launches"]
             n_launch += work["k_launch"]
         launches["n"] += n_launch
 
@@ -263,7 +285,8 @@ def run_gpu(args, rank, world, local_rank):
                            int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
 
     def timed_device():
-        step_device(probe=True)
+        for _ in range(len(pool)):       # probe pass: one untimed step per pool frame, counters read back
+            step_device(probe=True)
         for _ in range(args.warmup):
             flush_buf.zero_()
             step_device()
@@ -273,12 +296,14 @@ def run_gpu(args, rank, world, local_rank):
         barrier()
         eng.kernel_times()               # reset the library's per-launch event record
         launches["n"] = 0
+        work["pairs_total"] = sum(pool_pairs[(rank + seq["s"] + k) % len(pool)] for k in range(args.steps))
+        work["pairs"] = work["pairs_total"] / args.steps
         sampler.start()
         for a, b in evs[:-1]:
             flush_buf.zero_()            # L2 flush, outside the per-step event bracket
             a.record()
-            drain()                      # previous frame's histogram gather (timed if it is late)
-            step_device()
+            drain(keep=GATHER_WINDOW)    # results are collected a few frames behind the integrator, so one
+            step_device()                # heavy frame on one rank does not stall the others at every step
             b.record()
         evs[-1][0].record()
         drain()                          # the last frame's gather, inside its own timed bracket
@@ -304,7 +329,8 @@ def run_gpu(args, rank, world, local_rank):
         t, v = pinned(a)
         keep.append(t)
         return v
-    hx, hq = pin(inp["x"]), pin(inp["Q"])
+    hcharges = [(pin(f["x"]), pin(f["Q"])) for f in pool]
+    hx, hq = hcharges[0]
     if kind == "topo":
         hseeds, hnit = pin(inp["seeds"]), pin(inp["n_iter"])
         h2d = hx.nbytes + hq.nbytes + hseeds.nbytes + hnit.nbytes + de.nbytes + ce.nbytes
@@ -323,7 +349,9 @@ def run_gpu(args, rank, world, local_rank):
         o_rows = pin(np.zeros((K, len(hseeds), 2), np.float32))
         o_counts = pin(np.zeros((K, 50, 50), np.int64))
         hnit_frames = pin(np.broadcast_to(inp["n_iter"], (K, len(hseeds))).copy())
-        frames = [(hx, hq)] * K
+        e2e_ids = [(rank + k) % len(pool) for k in range(K)]            # the same rotation as the device arm
+        frames = [hcharges[j] for j in e2e_ids]
+        work["pairs_e2e_total"] = sum(pool_pairs[j] for j in e2e_ids)
         h2d = hx.nbytes + hq.nbytes + hnit.nbytes + (hseeds.nbytes + de.nbytes + ce.nbytes) // K
     elif kind == "field":
         o_field = pin(np.zeros((len(hpts), 6), np.float32))
@@ -334,6 +362,9 @@ def run_gpu(args, rank, world, local_rank):
         return m.topo_hist_frames(frames[:k], hseeds, hnit_frames[:k], de, ce, step_size=inp["h"],
                                   dimensions=inp["dims"], want_rows=True, rows_out=o_rows[:k],
                                   counts_out=o_counts[:k])
+
+    if kind != "topo":
+        work["pairs_e2e_total"] = work["pairs"] * args.steps
 
     def step_e2e():
         m.set_charges(hx, hq)
@@ -359,12 +390,13 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- reduce over ranks ---------------------------------------------------------------------------
     tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
-    ww = torch.tensor([float(work["pairs"]), float(work["units"])], dtype=torch.float64, device=dev)
+    ww = torch.tensor([float(work["pairs_total"]), float(work["units"]), float(work["pairs_e2e_total"])],
+                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(ww, op=dist.ReduceOp.SUM)
     t_dev, t_e2e = float(tt[0]), float(tt[1])
-    pairs_all, units_all = float(ww[0]), float(ww[1])
+    pairs_all, units_all, pairs_e2e_all = float(ww[0]), float(ww[1]), float(ww[2])   # pairs: whole timed region
 
     if rank != 0:
         return None
@@ -376,7 +408,7 @@ def run_gpu(args, rank, world, local_rank):
     kt = kern_ms[0::2] if (kind == "topo" and len(kern_ms) == 2 * args.steps) else kern_ms
     k_ms = float(np.mean(kt))
     achieved = work["pairs"] * flops / (k_ms * 1e-3) / 1e12
-    value = pairs_all * args.steps / t_dev
+    value = pairs_all / t_dev
     line = {
         "metric": "pair-evals/s", "value": value, "unit": "pair-evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
@@ -386,12 +418,15 @@ def run_gpu(args, rank, world, local_rank):
                    "units_per_step_per_gpu": int(work["units"]),
                    "pair_evals_per_step_per_gpu": int(work["pairs"]),
                    "l2": "flushed between timed steps (256 MiB write)",
+                   "frames": (f"{len(pool)} jittered MD frames; rank r integrates frame (r + step) mod {len(pool)}; "
+                              "pair_evals_per_step_per_gpu is rank 0's mean over the timed steps"
+                              if kind == "topo" else "one frame per rank"),
                    "parallelism": f"frames sharded, 1 frame per GPU per step, x{world}"},
         "units_per_s": units_all * args.steps / t_dev,
         "units": "streamlines" if kind == "topo" else "grid points",
         "fp32_frac_of_nominal": value / world * flops / 1e12 / NOMINAL_FP32_TFLOPS,
         "clocks": clocks,
-        "e2e": {"value": pairs_all * args.steps / t_e2e, "unit": "pair-evals/s",
+        "e2e": {"value": pairs_e2e_all / t_e2e, "unit": "pair-evals/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": t_e2e / args.steps * 1e3,
                 "api": ("Math_ops.topo_hist_frames -> cpet_topo_hist_frames: one call, one frame per step, pinned "
