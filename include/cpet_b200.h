@@ -215,6 +215,17 @@ int cpet_chi2_matrix(cpet_ctx *ctx, int n_hists, int64_t n_bins, const double *H
 int cpet_write_rows(const char *path, const char *header, const void *data, int dtype,
                     int64_t n_rows, int n_cols, const char *fmt, int n_threads);
 
+/* The way back in: the parse make_histograms repeats three times per `.top` file (UC:603-607 count,
+ * UC:626-633 read, UC:690-698 read again): lines starting with '#' are skipped (blank lines too),
+ * the first n_cols whitespace-separated numbers of every other line are converted with a correctly
+ * rounded decimal->double conversion -- bit for bit the value Python's float() returns, "inf" /
+ * "-inf" / "nan" as np.savetxt writes them included -- and stored row-major in out (n_rows, n_cols)
+ * float64; further columns on a line are ignored like the reference's line[0], line[1].  Host
+ * code, all cores (n_threads <= 0).  cpet_count_rows sizes the array; cpet_read_rows fails with
+ * CPET_ERR_INVALID if the file holds another number of data lines or a line with fewer numbers. */
+int cpet_count_rows(const char *path, int64_t *n_rows, int n_threads);
+int cpet_read_rows(const char *path, int n_cols, int64_t n_rows, double *out, int n_threads);
+
 /* ---------------------------------------------------------------- measurement -------------- */
 /* Sustained non-tensor FP32 rate of this device from a register-resident FMA loop.
  * packed=0: FFMA, packed=1: FFMA2 (fma.rn.f32x2).  Returns TFLOP/s in *tflops (2 flop/FMA). */

@@ -81,6 +81,8 @@ SIGNATURES = {
     "cpet_chi2_matrix": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "cpet_write_rows": (c_int, [ctypes.c_char_p, ctypes.c_char_p, c_void_p, c_int, c_int64, c_int,
                                 ctypes.c_char_p, c_int]),
+    "cpet_count_rows": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int64), c_int]),
+    "cpet_read_rows": (c_int, [ctypes.c_char_p, c_int, c_int64, c_void_p, c_int]),
     "cpet_fp32_peak_probe": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(ctypes.c_double)]),
     "cpet_last_kernel_ms": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double)]),
     "cpet_kernel_times": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), c_int, ctypes.POINTER(c_int)]),

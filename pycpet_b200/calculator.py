@@ -150,16 +150,12 @@ def histogram2d_counts(values, nd, nc, d_range, c_range):
 
 
 def read_top_file(path):
-    """Parse a .top file (two columns dist, curv; '#' comments) into an (n,2) float64 array."""
-    rows = []
-    with open(path) as fh:
-        for ln in fh:
-            if ln.startswith("#"):
-                continue
-            a = ln.split()
-            if len(a) >= 2:
-                rows.append((float(a[0]), float(a[1])))
-    return np.asarray(rows, dtype=np.float64).reshape(-1, 2)
+    """Parse a .top file (two columns dist, curv; '#' comments) into an (n,2) float64 array: the
+    values the reference's `float(line.split()[k])` loops produce (UC:626-633), read by
+    cpet_read_rows on all host cores."""
+    from .io import read_topology
+
+    return read_topology(path)
 
 
 def bin_plan(topologies):

@@ -1,7 +1,10 @@
-"""Writers for the path's output files, byte-compatible with the reference's np.savetxt calls.
+"""Writers and readers for the path's output files, byte-compatible with the reference's np.savetxt
+calls and value-identical to its `float(line.split()[k])` parsing loops.
 
 * ``save_topology(path, hist)``         == ``np.savetxt(path, hist)``            (CPET/source/CPET.py:123)
 * ``save_numpy_as_dat(meta, volume, name)`` == CPET/utils/io.py:50-109 (same signature, same bytes)
+* ``read_rows(path, n_cols)`` / ``read_topology(path)`` == the parse loops of make_histograms
+  (CPET/utils/calculator.py:603-633, 690-698): '#' lines skipped, float() of the leading columns
 
 np.savetxt formats row by row in Python; for a 1,000,000-line `.top` that costs seconds, i.e. two
 orders of magnitude more than computing the lines on the GPU.  ``cpet_write_rows`` does the same
@@ -32,6 +35,24 @@ def write_rows(path, array, fmt="%.18e", header="", threads=0):
     a = np.ascontiguousarray(a)
     check(_lib.load().cpet_write_rows(os.fsencode(path), header.encode(), _lib.ptr(a), _DTYPES[a.dtype],
                                       a.shape[0], a.shape[1], fmt.encode(), int(threads)))
+
+
+def read_rows(path, n_cols=2, threads=0):
+    """The data lines of a text file ('#' lines and blank lines skipped) -> (n, n_cols) float64, the
+    first n_cols numbers of every line converted exactly as Python's float() converts them."""
+    import ctypes
+
+    L = _lib.load()
+    n = ctypes.c_int64(0)
+    check(L.cpet_count_rows(os.fsencode(path), ctypes.byref(n), int(threads)))
+    out = np.empty((n.value, int(n_cols)), dtype=np.float64)
+    check(L.cpet_read_rows(os.fsencode(path), int(n_cols), n.value, _lib.ptr(out), int(threads)))
+    return out
+
+
+def read_topology(path):
+    """`.top` file -> (n, 2) float64 [dist|curv] (what make_histograms parses, UC:626-633)."""
+    return read_rows(path, 2)
 
 
 def save_topology(path, hist):

@@ -52,3 +52,96 @@ def test_writer_is_faster_than_savetxt(tmp_path):
     t0 = time.perf_counter(); pio.save_topology(str(tmp_path / "b.top"), hist); t_c = time.perf_counter() - t0
     assert (tmp_path / "a.top").read_bytes() == (tmp_path / "b.top").read_bytes()
     assert t_c < t_np
+
+
+def _reference_parse(path):
+    """The reference's own loop (CPET/utils/calculator.py:626-633), restated; a blank line, on which
+    the reference raises IndexError, is skipped here as the reader skips it."""
+    d, c = [], []
+    with open(path) as fh:
+        for line in fh:
+            if line.startswith("#"):
+                continue
+            line = line.strip().split()
+            if not line:
+                continue
+            d.append(float(line[0]))
+            c.append(float(line[1]))
+    return np.column_stack([d, c]) if d else np.zeros((0, 2))
+
+
+def test_top_reader_matches_float_parsing(tmp_path):
+    rng = np.random.default_rng(3)
+    hist = np.column_stack([rng.gamma(2.0, 0.3, 150_000), rng.gamma(1.5, 0.4, 150_000)]).astype(np.float32)
+    hist[5] = [0.0, -0.0]
+    hist[6] = [np.inf, -np.inf]
+    hist[7] = [np.nan, 1e-38]
+    hist[8] = [3.4e38, 1.4e-45]
+    p = tmp_path / "a.top"
+    np.savetxt(p, hist)                                   # several MB: more than one reader span
+    got = pio.read_topology(str(p))
+    want = _reference_parse(p)
+    assert got.dtype == np.float64 and got.shape == want.shape
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64)) or \
+        np.array_equal(got[~np.isnan(want)].view(np.uint64), want[~np.isnan(want)].view(np.uint64))
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got.astype(np.float32)[~np.isnan(hist)], hist[~np.isnan(hist)])   # text round trip
+
+
+def test_top_reader_edge_cases(tmp_path):
+    p = tmp_path / "b.top"
+    # comments, blank line, CRLF, tabs, '+' sign, third column ignored, doubles that need correct
+    # rounding, overflow / underflow, no trailing newline
+    p.write_bytes(b"# header\n#another\n\n1.0 2.0\r\n\t+3.5e-1\t  -4.25E+2  99\n"
+                  b"0.1 0.30000000000000004\n1e400 -1e400\n1e-400 4.9406564584124654e-324\n"
+                  b"2.2250738585072011e-308 1.7976931348623157e308\n7 8")
+    got = pio.read_rows(str(p), 2)
+    want = _reference_parse(p)
+    assert got.shape == (7, 2)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    assert pio.read_rows(str(p), 1).shape == (7, 1)
+    # empty and comment-only files
+    e = tmp_path / "e.top"
+    e.write_bytes(b"")
+    assert pio.read_topology(str(e)).shape == (0, 2)
+    e.write_bytes(b"# nothing\n")
+    assert pio.read_topology(str(e)).shape == (0, 2)
+
+
+def test_top_reader_errors(tmp_path):
+    import pytest
+
+    from pycpet_b200 import CpetError
+
+    p = tmp_path / "bad.top"
+    p.write_bytes(b"1.0 2.0\n3.0\n")
+    with pytest.raises(CpetError, match="data line 2"):
+        pio.read_topology(str(p))
+    p.write_bytes(b"1.0 2.0\n3.0 abc\n")
+    with pytest.raises(CpetError):
+        pio.read_topology(str(p))
+    with pytest.raises(CpetError, match="cannot open"):
+        pio.read_topology(str(tmp_path / "missing.top"))
+
+
+def test_reader_is_faster_than_the_python_loop(tmp_path):
+    hist = np.random.default_rng(4).random((200_000, 2)).astype(np.float32)
+    p = tmp_path / "c.top"
+    pio.save_topology(str(p), hist)
+    t0 = time.perf_counter(); want = _reference_parse(p); t_py = time.perf_counter() - t0
+    t0 = time.perf_counter(); got = pio.read_topology(str(p)); t_c = time.perf_counter() - t0
+    assert np.array_equal(got, want)
+    assert t_c < t_py
+
+
+def test_writer_formats_agree_with_savetxt(tmp_path):
+    """'%.Ne' / '%.Nf' take the std::to_chars path, everything else snprintf: same bytes either way."""
+    rng = np.random.default_rng(5)
+    v = np.concatenate([rng.normal(0, 1, 4000) * 10.0 ** rng.integers(-300, 300, 4000),
+                        [0.0, -0.0, np.inf, -np.inf, np.nan, -np.nan, 7.0, 5e-324, 1.7976931348623157e308, 0.0005, 0.0015,
+                         -0.0004, 2.5, 3.5, 1e22, 123456789012345678.0]]).reshape(-1, 2)
+    a, b = tmp_path / "a.txt", tmp_path / "b.txt"
+    for fmt in ("%.18e", "%.3f", "%.0f", "%.0e", "%.6e", "%.25e", "%g", "%12.5f", "%+.4e", "%.10g"):
+        np.savetxt(a, v, fmt=fmt)
+        pio.write_rows(str(b), v, fmt=fmt)
+        assert a.read_bytes() == b.read_bytes(), fmt
