@@ -88,18 +88,28 @@ class ClockSampler:
     BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
     NOTE = {"sw_power_cap": 0x4, "hw_power_brake": 0x80}
 
-    def __init__(self, index: int):
-        self.index = index
+    def __init__(self, local_rank: int):
         self.samples, self.reasons = [], set()
         self.max_mhz = None
         self._stop = threading.Event()
         self._thr = None
+        # NVML numbers the physical devices; CUDA_VISIBLE_DEVICES (indices or GPU-/MIG- UUIDs) maps
+        # this process's local rank onto them
+        entry = None
+        vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        if local_rank < len(vis):
+            entry = vis[local_rank]
         try:
             import pynvml
 
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            if entry is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            elif entry.isdigit():
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(int(entry))
+            else:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(entry.encode())
             self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.nv = None
@@ -184,6 +194,27 @@ def pinned(a):
     return t, t.numpy()
 
 
+# the three places run_gpu touches torch.cuda directly (tests/test_bench_dryrun.py swaps them, the
+# Engine and Math_ops for host stand-ins to exercise the accounting and the N > 1 flow over gloo)
+def _device(local_rank):
+    import torch
+
+    torch.cuda.set_device(local_rank)
+    return torch.device("cuda", local_rank)
+
+
+def _event():
+    import torch
+
+    return torch.cuda.Event(enable_timing=True)
+
+
+def _sync():
+    import torch
+
+    torch.cuda.synchronize()
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -192,8 +223,7 @@ def run_gpu(args, rank, world, local_rank):
     from pycpet_b200.device import Engine
 
     kind, desc, prm = WORKLOADS[args.workload]
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    dev = _device(local_rank)
     # Streamline workloads run a trajectory: POOL frames (base charge set + per-frame jitter),
     # rank r integrates frame (r + s) mod POOL at step s -- a different frame on every GPU at every step, and
     # the same mix of frames on every rank whatever N is.  Grid workloads: one frame per rank (equal work).
@@ -276,13 +306,12 @@ def run_gpu(args, rank, world, local_rank):
         launches["n"] += n_launch
 
     def barrier():
-        torch.cuda.synchronize()
+        _sync()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        _sync()
 
-    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    sampler = ClockSampler(local_rank)
 
     def timed_device():
         for _ in range(len(pool)):       # probe pass: one untimed step per pool frame, counters read back
@@ -291,8 +320,7 @@ def run_gpu(args, rank, world, local_rank):
             flush_buf.zero_()
             step_device()
         drain()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-               for _ in range(args.steps + 1)]
+        evs = [(_event(), _event()) for _ in range(args.steps + 1)]
         barrier()
         eng.kernel_times()               # reset the library's per-launch event record
         launches["n"] = 0
@@ -384,7 +412,7 @@ def run_gpu(args, rank, world, local_rank):
     else:
         for _ in range(args.steps):
             res = step_e2e()
-    torch.cuda.synchronize()
+    _sync()
     t_e2e = time.perf_counter() - t0
     barrier()
 

@@ -1,0 +1,298 @@
+"""CPU: bench.run_gpu's control flow and accounting with the device swapped for host stand-ins.
+
+Nothing here computes a field: the Engine / Math_ops stand-ins only count calls and report a fixed,
+frame-dependent amount of work, and CUDA events are replaced by a fake clock.  What is checked is
+bench.py's own logic -- the frame rotation, that `value` is (work of the timed steps) / (timed
+seconds), the JSON contract keys, and (world_size 2 over gloo) the asynchronous histogram gathers,
+the max-over-ranks time and the sum-over-ranks work."""
+import argparse
+import json
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+STEP_MS = 2.0            # fake duration of every timed event bracket
+K_MS = 1.5               # fake duration of the dominant kernel
+
+
+class FakeClock:
+    now = 0.0
+
+
+class FakeEvent:
+    def __init__(self):
+        self.t = None
+
+    def record(self):
+        FakeClock.now += STEP_MS / 2.0
+        self.t = FakeClock.now
+
+    def elapsed_time(self, other):
+        return other.t - self.t
+
+
+class FakeEngine:
+    """Stand-in for pycpet_b200.device.Engine: same method names, no device."""
+    instances = []
+
+    def __init__(self, device=None, stream=None):
+        self.frame_m = None
+        self.frame_tag = 0.0
+        self.times = []
+        self.calls = {"set_charges": 0, "topo_batch": 0, "hist2d": 0, "grid": 0}
+        self.frames_seen = []
+        FakeEngine.instances.append(self)
+
+    def set_tuning(self, **kv):
+        pass
+
+    def set_charges(self, x, Q):
+        self.calls["set_charges"] += 1
+        self.frame_m = int(Q.numel())
+        self.frame_tag = float(x.reshape(-1)[0])       # distinguishes the jittered frames
+        self.frames_seen.append(self.frame_tag)
+
+    def _pairs(self, units):
+        # a frame-dependent amount of work, as box exits make it on the device
+        return int(units * self.frame_m * (10 + int(abs(self.frame_tag) * 1000) % 7))
+
+    def topo_batch(self, seeds, n_iter, step_size, dimensions, second_diff=False, out=None, steps=None):
+        self.calls["topo_batch"] += 1
+        self.units = int(seeds.shape[0])
+        self.times.append(K_MS)
+        out.zero_()
+        return out
+
+    def hist2d(self, values, d_edges, c_edges, out=None):
+        self.calls["hist2d"] += 1
+        self.times.append(0.01)
+        out.fill_(self.calls["hist2d"])
+        return out
+
+    def field_grid(self, x0, soften=True, concat=False, out=None):
+        self.calls["grid"] += 1
+        self.units = int(x0.shape[0])
+        self.times.append(K_MS)
+        return out
+
+    def field_lattice(self, xs, ys, zs, soften=True, concat=False, out=None):
+        self.calls["grid"] += 1
+        self.units = int(xs.numel() * ys.numel() * zs.numel())
+        self.times.append(K_MS)
+        return out
+
+    def esp_grid(self, x0, concat_half=False, out=None):
+        self.calls["grid"] += 1
+        self.units = int(x0.shape[0])
+        self.times.append(K_MS)
+        return out
+
+    def last_counters(self):
+        return {"launches": 4, "pair_evals": self._pairs(self.units), "field_evals": 0}
+
+    def kernel_times(self):
+        t, self.times = self.times, []
+        return t
+
+    def fp32_peak_tflops(self, packed=True, iters=4096):
+        return 73.4 if packed else 72.4
+
+
+class FakeMath:
+    """Stand-in for pycpet_b200.Math_ops (host-pointer arm)."""
+    frames_calls = []
+
+    def __init__(self, shared_loc=None, device=None):
+        pass
+
+    def set_charges(self, x, Q):
+        pass
+
+    def topo_hist_frames(self, frames, seeds, n_iter, d_edges, c_edges, step_size=0.1, dimensions=(1, 1, 1),
+                         second_diff=False, want_rows=False, rows_out=None, counts_out=None):
+        assert n_iter.shape == (len(frames), len(seeds))
+        assert rows_out.shape == (len(frames), len(seeds), 2) and counts_out.shape[0] == len(frames)
+        FakeMath.frames_calls.append([float(np.asarray(fx).reshape(-1)[0]) for fx, _ in frames])
+        return rows_out, counts_out
+
+    def field_grid(self, x_0, x=None, Q=None, soften=True, concat=False, out=None):
+        return out
+
+    def esp_grid(self, x_0, x=None, Q=None, concat_half=False, out=None):
+        return out
+
+
+def _install(monkey_set):
+    """Swap the device-touching pieces of bench.py and the package for the stand-ins."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench
+    import pycpet_b200
+    import pycpet_b200.device as pdev
+
+    def host_pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t, t.numpy()
+
+    monkey_set(bench, "_device", lambda local_rank: torch.device("cpu"))
+    monkey_set(bench, "_event", FakeEvent)
+    monkey_set(bench, "_sync", lambda: None)
+    monkey_set(bench, "pinned", host_pinned)
+    monkey_set(bench, "cpu_baseline", lambda *a, **k: {"value": 1.0, "unit": "pair-evals/s", "cores": 1,
+                                                        "kind": "port", "sample": "stub"})
+    monkey_set(pdev, "Engine", FakeEngine)
+    monkey_set(pycpet_b200, "Math_ops", FakeMath)
+    FakeEngine.instances.clear()
+    FakeMath.frames_calls.clear()
+    FakeClock.now = 0.0
+    # small shapes: 5^3 lines / points on a 300-charge frame
+    for name, (kind, desc, prm) in list(bench.WORKLOADS.items()):
+        small = dict(prm, m=300, n_axis=5)
+        monkey_set(bench.WORKLOADS, name, (kind, desc, small), item=True)
+    return bench
+
+
+def _args(workload, steps=5, warmup=3):
+    return argparse.Namespace(gpus=1, steps=steps, warmup=warmup, workload=workload, impl="b200", cpu_seconds=None)
+
+
+CONTRACT_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                 "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline")
+
+
+@pytest.fixture
+def bench_mod(monkeypatch):
+    def monkey_set(obj, name, value, item=False):
+        if item:
+            monkeypatch.setitem(obj, name, value)
+        else:
+            monkeypatch.setattr(obj, name, value)
+    return _install(monkey_set)
+
+
+def test_topo_accounting_single_rank(bench_mod):
+    bench = bench_mod
+    steps, warmup = 5, 3
+    line = bench.run_gpu(_args("topo3a", steps, warmup), rank=0, world=1, local_rank=0)
+    json.dumps(line)                                         # serialisable
+    for k in CONTRACT_KEYS + ("cpu_baseline",):
+        assert k in line, k
+    assert line["n_gpus"] == 1 and line["steps"] == steps and line["vs_baseline"] is None
+    assert line["higher_is_better"] is True and line["scaling"] == "weak" and line["dtype"] == "f32"
+    assert "workload" in line["config"] and "model" not in line["config"]
+    eng = FakeEngine.instances[0]
+    pool = bench.FRAME_POOL
+    # probe pass (one step per pool frame) + warm-up + timed steps, each one set_charges -> topo -> hist
+    assert eng.calls["set_charges"] == eng.calls["topo_batch"] == eng.calls["hist2d"] == pool + warmup + steps
+    assert len(set(eng.frames_seen[:pool])) == pool          # the probe pass visits every pool frame once
+    # rotation continues across warm-up into the timed steps: frame (rank + s) mod POOL at step s
+    assert eng.frames_seen[pool:2 * pool][:warmup + steps] == (eng.frames_seen[:pool] * 2)[:warmup + steps]
+    # value = pair-evals of exactly the timed steps / the fake clock's timed seconds
+    tags = eng.frames_seen[-steps:]
+    by_tag = {}
+    for t in eng.frames_seen[:pool]:
+        eng.frame_tag = t
+        by_tag[t] = eng._pairs(125)
+    want_pairs = sum(by_tag[t] for t in tags)
+    timed_s = (steps + 1) * (STEP_MS / 2.0) * 1e-3           # one a->b bracket per step + the drain bracket
+    assert line["value"] == pytest.approx(want_pairs / timed_s, rel=1e-12)
+    assert line["ms_per_step"] == pytest.approx(timed_s / steps * 1e3)
+    assert line["config"]["units_per_step_per_gpu"] == 125
+    assert line["units_per_s"] == pytest.approx(125 * steps / timed_s)
+    # launches claimed for the timed region: pack + K2 launches + histogram per step
+    assert line["gpu_launches"] == steps * (1 + 4 + 1)
+    # roofline: 20 flop x mean pair-evals per timed step / the integrator's own duration
+    r = line["roofline"]
+    assert r["kernel"] == "k2w_topo_kernel" and r["kernel_ms"] == pytest.approx(K_MS)
+    assert r["achieved"] == pytest.approx(want_pairs / steps * 20.0 / (K_MS * 1e-3) / 1e12)
+    assert r["peak"] == 73.4 and r["frac"] == pytest.approx(r["achieved"] / 73.4)
+    # end-to-end arm: one warm-up call and ONE timed call of `steps` frames, in the rotation of the device arm
+    assert [len(c) for c in FakeMath.frames_calls] == [3, steps]
+    assert FakeMath.frames_calls[1] == (eng.frames_seen[:pool] * 2)[:steps]
+    e = line["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 125 * 8 + 50 * 50 * 8
+    assert e["value"] > 0 and e["unit"] == line["unit"]
+
+
+@pytest.mark.parametrize("workload,kernel", [("volume", "k1_grid_kernel"), ("esp101", "k1_grid_kernel"),
+                                             ("volume2a", "k1_grid_kernel")])
+def test_grid_accounting_single_rank(bench_mod, workload, kernel):
+    bench = bench_mod
+    steps = 4
+    line = bench.run_gpu(_args(workload, steps, 3), rank=0, world=1, local_rank=0)
+    json.dumps(line)
+    for k in CONTRACT_KEYS:
+        assert k in line, k
+    eng = FakeEngine.instances[0]
+    assert eng.calls["grid"] == 1 + 3 + steps and eng.calls["topo_batch"] == 0      # one frame per rank: one probe
+    pairs = eng._pairs(125)
+    timed_s = (steps + 1) * (STEP_MS / 2.0) * 1e-3
+    assert line["value"] == pytest.approx(pairs * steps / timed_s)
+    assert line["roofline"]["kernel"] == kernel
+    flops = 11.0 if workload == "esp101" else 20.0
+    assert line["roofline"]["flops_per_pair"] == flops
+    assert line["roofline"]["achieved"] == pytest.approx(pairs * flops / (K_MS * 1e-3) / 1e12)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, size, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+
+    def monkey_set(obj, name, value, item=False):
+        if item:
+            obj[name] = value
+        else:
+            setattr(obj, name, value)
+
+    bench = _install(monkey_set)
+    steps = 7                                     # more than GATHER_WINDOW: the windowed drain is exercised
+    line = bench.run_gpu(_args("topo3a", steps, 3), rank=rank, world=size, local_rank=0)
+    eng = FakeEngine.instances[0]
+    by_tag = {}
+    for t in eng.frames_seen[:bench.FRAME_POOL]:
+        eng.frame_tag = t
+        by_tag[t] = eng._pairs(125)
+    mine = sum(by_tag[t] for t in eng.frames_seen[-steps:])
+    both = torch.tensor([float(mine)], dtype=torch.float64)
+    dist.all_reduce(both)
+    if rank == 0:
+        with open(os.path.join(tmp, "line.json"), "w") as fh:
+            json.dump({"line": line, "pairs_all": float(both[0]), "first": eng.frames_seen[0]}, fh)
+    else:
+        assert line is None                       # only rank 0 reports
+        with open(os.path.join(tmp, "rank1.json"), "w") as fh:
+            json.dump({"first": eng.frames_seen[0]}, fh)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_over_gloo(tmp_path):
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    d = json.load(open(tmp_path / "line.json"))
+    line = d["line"]
+    for k in CONTRACT_KEYS:
+        assert k in line, k
+    assert "cpu_baseline" not in line             # rank 0 times the CPU reference at N = 1 only
+    assert line["n_gpus"] == 2
+    timed_s = (7 + 1) * (STEP_MS / 2.0) * 1e-3    # both ranks report the same fake time; the max is that time
+    assert line["value"] == pytest.approx(d["pairs_all"] / timed_s)          # work summed over ranks
+    assert line["units_per_s"] == pytest.approx(2 * 125 * 7 / timed_s)
+    # the two ranks start the rotation on different frames
+    assert json.load(open(tmp_path / "rank1.json"))["first"] != d["first"]
