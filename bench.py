@@ -485,6 +485,9 @@ def run_gpu(args, rank, world, local_rank):
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle/_ref = the reference's own math_module.c; oracle port otherwise)
 # ------------------------------------------------------------------------------------------------
+_CREDIT = {}     # (frame, sample size) -> pair-evaluations credited; the accounting pass runs once per sample
+
+
 def cpu_run_sample(kind, inp, n_units, threads, use_ref):
     from oracle import f64, ref
 
@@ -492,8 +495,11 @@ def cpu_run_sample(kind, inp, n_units, threads, use_ref):
     if kind == "topo":
         sel = np.linspace(0, len(inp["seeds"]) - 1, n_units).astype(np.int64)
         seeds, n_iter = inp["seeds"][sel], inp["n_iter"][sel]
-        _, steps = f64.topo_batch(seeds, n_iter, x, Q, inp["h"], inp["dims"])       # work accounting only
-        credited = float((steps.astype(np.int64) + 2).sum()) * len(Q)
+        key = (id(inp["x"]), int(n_units))
+        if key not in _CREDIT:      # steps taken per line (float64 port, all cores), work accounting only
+            _, steps = f64.topo_batch(seeds, n_iter, x, Q, inp["h"], inp["dims"])
+            _CREDIT[key] = float((steps.astype(np.int64) + 2).sum()) * len(Q)
+        credited = _CREDIT[key]
         t0 = time.perf_counter()
         if use_ref:
             ref.topo(seeds, n_iter, x, Q, inp["h"], inp["dims"], threads=threads)
@@ -510,17 +516,47 @@ def cpu_run_sample(kind, inp, n_units, threads, use_ref):
     return time.perf_counter() - t0, float(len(pts)) * len(Q)
 
 
+def host_cores() -> int:
+    """Cores this process may actually use: the affinity mask, capped by a cgroup v2 CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def cpu_baseline(kind, prm, inp, budget_s=12.0, steps=1, warmup=0):
     from oracle import f64, ref
 
     use_ref = ref.available()
-    threads = os.cpu_count() or 1
-    if not use_ref:
-        threads = f64.num_threads()
+    threads = host_cores()
+    # the float64 port (work accounting; the timed arm itself when oracle/_ref is absent) runs on all
+    # cores whatever OMP_NUM_THREADS says -- torchrun exports 1, and so does this file at N = 1
+    f64.set_num_threads(threads)
     total = len(inp["seeds"]) if kind == "topo" else len(inp["points"])
     probe = min(total, 64 * threads)
-    t, w = cpu_run_sample(kind, inp, probe, threads, use_ref)            # calibration (also warms up)
-    n = int(min(total, max(probe, probe * budget_s / max(t, 1e-6))))
+    # calibration, repeated until two passes agree: the first parallel burst of a process runs several
+    # times slower than the steady state (cores idle until then), which would both shrink the sample
+    # and under-report the reference
+    t, w = cpu_run_sample(kind, inp, probe, threads, use_ref)
+    for _ in range(8):
+        t2, w = cpu_run_sample(kind, inp, probe, threads, use_ref)
+        settled = t2 > 0.8 * t
+        t = min(t, t2)
+        if settled:
+            break
+    # second stage: about one second of work, whose rate sizes the sample (the probe is too short to
+    # be a steady-state rate on a many-core box)
+    n1 = int(min(total, max(probe, probe * min(1.0, budget_s) / max(t, 1e-6))))
+    t1, _ = cpu_run_sample(kind, inp, n1, threads, use_ref)
+    n = int(min(total, max(probe, n1 * budget_s / max(t1, 1e-6))))
     for _ in range(warmup):
         cpu_run_sample(kind, inp, n, threads, use_ref)
     tt, ww = 0.0, 0.0

@@ -35,6 +35,8 @@ def lib():
         build()
         L = ctypes.CDLL(_SO)
         L.orc_num_threads.restype = ctypes.c_int
+        L.orc_set_num_threads.restype = None
+        L.orc_set_num_threads.argtypes = [ctypes.c_int]
         L.orc_field_grid.restype = None
         L.orc_field_grid.argtypes = [ctypes.c_int, ctypes.c_int, _f32p, _f32p, _f32p,
                                      ctypes.c_int, _f64p]
@@ -54,6 +56,11 @@ def lib():
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the following calls, independent of OMP_NUM_THREADS."""
+    lib().orc_set_num_threads(int(n))
 
 
 def _f32(a, shape=None):
