@@ -78,7 +78,10 @@ int cpet_last_counters(cpet_ctx *ctx, int64_t out[3]);
 
 /* Upload (and pack) the charge set of one frame: x (M,3) float32 row-major, Q (M,) float32 --
  * the `x`, `Q` arguments every reference entry point takes (OPS:250-375).  Done once per frame;
- * all following calls on this context use it. */
+ * all following calls on this context use it.  The host form enqueues the upload and returns: with
+ * pageable memory (NumPy arrays) the data has been staged by then; page-locked x / Q must stay
+ * untouched until the next host-pointer call on this context or cpet_sync() returns.  Every other
+ * host-pointer entry point drains its stream before returning, on error paths too. */
 int cpet_set_charges(cpet_ctx *ctx, int n_charges, const float *x, const float *Q);
 int cpet_set_charges_dev(cpet_ctx *ctx, int n_charges, const float *d_x, const float *d_Q);
 

@@ -120,6 +120,18 @@ static int make_ctx(int device, void* stream, bool borrow, cpet_ctx** out) {
     return CPET_OK;
 }
 
+// Host-pointer entry points enqueue copies that reference the caller's buffers.  Whatever path such
+// a call leaves on, its stream is drained first: a caller may free (pinned) buffers right after an
+// error return.  The success paths synchronise themselves and disarm the guard.
+struct DrainOnExit {
+    cudaStream_t s;
+    bool armed = true;
+    explicit DrainOnExit(cudaStream_t st) : s(st) {}
+    ~DrainOnExit() {
+        if (armed) cudaStreamSynchronize(s);
+    }
+};
+
 #define CTX_GUARD(c)                                                                     \
     CPET_REQUIRE((c) != nullptr, CPET_ERR_INVALID, "context is NULL");                   \
     CPET_CUDA_TRY(cudaSetDevice((c)->device))
@@ -303,6 +315,7 @@ int cpet_field_grid(cpet_ctx* c, int n_points, const float* x0, unsigned flags, 
     const size_t out_floats = (flags & CPET_OUT_CONCAT) ? 6 * n : 3 * n;
     if (int rc = c->in0.reserve(sizeof(float) * 3 * n)) return rc;
     if (int rc = c->out0.reserve(sizeof(float) * out_floats)) return rc;
+    DrainOnExit drain(c->stream);
     CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, x0, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
     // The reference only ever hands over mesh.reshape(-1,3) (UC:442): recognise box meshes here and
     // give them the lattice kernel (bit-identical results, a quarter fewer FP32 instructions).
@@ -322,6 +335,7 @@ int cpet_field_grid(cpet_ctx* c, int n_points, const float* x0, unsigned flags, 
     }
     CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, sizeof(float) * out_floats, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    drain.armed = false;
     return CPET_OK;
 }
 
@@ -342,6 +356,7 @@ int cpet_esp_grid(cpet_ctx* c, int n_points, const float* x0, unsigned flags, vo
     const size_t out_bytes = (flags & CPET_OUT_CONCAT) ? 8 * n : 4 * n;
     if (int rc = c->in0.reserve(sizeof(float) * 3 * n)) return rc;
     if (int rc = c->out0.reserve(out_bytes)) return rc;
+    DrainOnExit drain(c->stream);
     CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, x0, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
     // box meshes (UC:450-475 hands over mesh.reshape(-1,3)) get the lattice kernel, as in cpet_field_grid
     int is_lat = 0, nx = 0, ny = 0, nz = 0;
@@ -360,6 +375,7 @@ int cpet_esp_grid(cpet_ctx* c, int n_points, const float* x0, unsigned flags, vo
     }
     CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    drain.armed = false;
     return CPET_OK;
 }
 
@@ -398,12 +414,14 @@ static int lattice_host(cpet_ctx* c, int is_esp, int nx, int ny, int nz, const f
     float* d_xs = c->in0.as<float>();
     float* d_ys = d_xs + nx;
     float* d_zs = d_ys + ny;
+    DrainOnExit drain(c->stream);
     CPET_CUDA_TRY(cudaMemcpyAsync(d_xs, xs, sizeof(float) * nx, cudaMemcpyHostToDevice, c->stream));
     CPET_CUDA_TRY(cudaMemcpyAsync(d_ys, ys, sizeof(float) * ny, cudaMemcpyHostToDevice, c->stream));
     CPET_CUDA_TRY(cudaMemcpyAsync(d_zs, zs, sizeof(float) * nz, cudaMemcpyHostToDevice, c->stream));
     if (int rc = lattice_dev(c, is_esp, nx, ny, nz, d_xs, d_ys, d_zs, flags, c->out0.p)) return rc;
     CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, ob, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    drain.armed = false;
     return CPET_OK;
 }
 
@@ -439,10 +457,12 @@ int cpet_propagate(cpet_ctx* c, int n_points, const float* x0, float step_size, 
     const size_t n = (size_t)n_points;
     if (int rc = c->in0.reserve(sizeof(float) * 3 * n)) return rc;
     if (int rc = c->out0.reserve(sizeof(float) * 3 * n)) return rc;
+    DrainOnExit drain(c->stream);
     CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, x0, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
     if (int rc = cpet_propagate_dev(c, n_points, c->in0.as<float>(), step_size, c->out0.as<float>())) return rc;
     CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    drain.armed = false;
     return CPET_OK;
 }
 
@@ -470,6 +490,7 @@ int cpet_topo_batch(cpet_ctx* c, int n_lines, const float* seeds, const int32_t*
     if (int rc = c->in1.reserve(sizeof(int32_t) * n)) return rc;
     if (int rc = c->out0.reserve(sizeof(float) * 2 * n)) return rc;
     if (steps) { if (int rc = c->out1.reserve(sizeof(int32_t) * n)) return rc; }
+    DrainOnExit drain(c->stream);
     CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, seeds, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
     CPET_CUDA_TRY(cudaMemcpyAsync(c->in1.p, n_iter, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
     if (int rc = cpet_topo_batch_dev(c, n_lines, c->in0.as<float>(), c->in1.as<int32_t>(), step_size, dims,
@@ -479,6 +500,7 @@ int cpet_topo_batch(cpet_ctx* c, int n_lines, const float* seeds, const int32_t*
     if (steps)
         CPET_CUDA_TRY(cudaMemcpyAsync(steps, c->out1.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    drain.armed = false;
     return CPET_OK;
 }
 
@@ -514,6 +536,7 @@ static int hist2d_host(cpet_ctx* c, int n_frames, int64_t n_per_frame, const voi
     CPET_REQUIRE(n_frames >= 0 && n_per_frame >= 0, CPET_ERR_INVALID, "negative sizes");
     CPET_REQUIRE(counts != nullptr, CPET_ERR_INVALID, "counts is NULL");
     CPET_REQUIRE((int64_t)n_frames * n_per_frame == 0 || values, CPET_ERR_INVALID, "values is NULL");
+    DrainOnExit drain(c->stream);
     const double *dd, *dc;
     if (int rc = upload_edges(c, nd, d_edges, nc, c_edges, &dd, &dc)) return rc;
     const size_t nval = (size_t)n_frames * (size_t)n_per_frame * 2;
@@ -527,6 +550,7 @@ static int hist2d_host(cpet_ctx* c, int n_frames, int64_t n_per_frame, const voi
         return rc;
     if (cbytes) CPET_CUDA_TRY(cudaMemcpyAsync(counts, c->out0.p, cbytes, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    drain.armed = false;
     return CPET_OK;
 }
 
@@ -547,6 +571,7 @@ int cpet_topo_hist(cpet_ctx* c, int n_lines, const float* seeds, const int32_t* 
     CPET_REQUIRE(n_lines >= 0, CPET_ERR_INVALID, "n_lines < 0");
     CPET_REQUIRE(n_lines == 0 || (seeds && n_iter), CPET_ERR_INVALID, "NULL seed/n_iter arrays");
     CPET_REQUIRE(counts != nullptr, CPET_ERR_INVALID, "counts is NULL");
+    DrainOnExit drain(c->stream);
     const double *dd, *dc;
     if (int rc = upload_edges(c, nd, d_edges, nc, c_edges, &dd, &dc)) return rc;
     const size_t n = (size_t)(n_lines > 0 ? n_lines : 1);
@@ -576,6 +601,7 @@ int cpet_topo_hist(cpet_ctx* c, int n_lines, const float* seeds, const int32_t* 
         CPET_CUDA_TRY(cudaMemcpyAsync(steps, c->out1.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaMemcpyAsync(counts, c->work0.p, cbytes, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    drain.armed = false;
     return CPET_OK;
 }
 
@@ -771,10 +797,12 @@ int cpet_chi2_matrix(cpet_ctx* c, int n_hists, int64_t n_bins, const double* H, 
     const size_t ob = sizeof(double) * (size_t)n_hists * n_hists;
     if (int rc = c->in0.reserve(hb ? hb : 8)) return rc;
     if (int rc = c->out0.reserve(ob)) return rc;
+    DrainOnExit drain(c->stream);
     if (hb) CPET_CUDA_TRY(cudaMemcpyAsync(c->in0.p, H, hb, cudaMemcpyHostToDevice, c->stream));
     if (int rc = launch_chi2(c, n_hists, n_bins, c->in0.as<double>(), c->out0.as<double>())) return rc;
     CPET_CUDA_TRY(cudaMemcpyAsync(out, c->out0.p, ob, cudaMemcpyDeviceToHost, c->stream));
     CPET_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    drain.armed = false;
     return CPET_OK;
 }
 
