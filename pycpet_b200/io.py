@@ -50,14 +50,33 @@ def read_rows(path, n_cols=2, threads=0):
     return out
 
 
-def read_topology(path):
-    """`.top` file -> (n, 2) float64 [dist|curv] (what make_histograms parses, UC:626-633)."""
+def _side_channel(path):
+    return path + ".npy"
+
+
+def read_topology(path, use_binary=True):
+    """`.top` file -> (n, 2) float64 [dist|curv] (what make_histograms parses, UC:626-633).
+    When save_topology(..., binary=True) left a `<name>.top.npy` next to the text and it is not older
+    than the text, the rows come from there: '%.18e' prints a float32 exactly, so both routes give
+    the same float64 values bit for bit."""
+    npy = _side_channel(path)
+    if use_binary and os.path.exists(npy) and (not os.path.exists(path) or
+                                                os.path.getmtime(npy) >= os.path.getmtime(path)):
+        return np.load(npy).astype(np.float64).reshape(-1, 2)
     return read_rows(path, 2)
 
 
-def save_topology(path, hist):
-    """`.top` file: two columns dist, curv in '%.18e' -- the bytes np.savetxt(path, hist) writes."""
+def save_topology(path, hist, binary=False):
+    """`.top` file: two columns dist, curv in '%.18e' -- the bytes np.savetxt(path, hist) writes.
+    binary=True also leaves the float32 rows as `<name>.top.npy` (written after the text, so it is
+    never older); the name does not end in "top", so the dispatcher's resume rule
+    (CPET/source/CPET.py:118-119) does not see it."""
     write_rows(path, hist, fmt="%.18e")
+    if binary:
+        a = np.asarray(hist)
+        if a.dtype != np.float32:
+            raise ValueError("the binary side channel holds float32 rows (what the integrator returns)")
+        np.save(_side_channel(path), np.ascontiguousarray(a).reshape(-1, 2))
 
 
 def dat_header(meta_data):

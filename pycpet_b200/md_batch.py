@@ -70,11 +70,13 @@ def _flush(math, frames, d_edges, c_edges, second_diff):
 
 def run_topo_frames(options, files, outputpath=None, d_edges=None, c_edges=None, workers=None,
                     chunk=16, math=None, prepare=prepare_frame, initializer=None, initargs=(),
-                    second_diff=False, skip_done=True, keep_rows=False):
+                    second_diff=False, skip_done=True, keep_rows=False, binary=False):
     """Topology of every structure in `files` (the loop of CPET.run_topo as one pipelined batch).
 
     options     the reference's options dict, handed unchanged to `prepare(options, path)`
     outputpath  directory for `<protein>.top` files (None: nothing is written)
+    binary      also leave `<protein>.top.npy` (float32 rows) next to every text file; make_histograms
+                then skips the text parse (same values bit for bit)
     d_edges, c_edges  optional shared bin edges; with them the (nd,nc) int64 counts of every frame
                 are returned as well (np.histogram2d binning)
     workers     preparation processes (default: all host cores but one); 0 prepares in-process.
@@ -109,7 +111,7 @@ def run_topo_frames(options, files, outputpath=None, d_edges=None, c_edges=None,
     def emit(batch):
         for path, rows, counts in _flush(math, batch, d_edges, c_edges, second_diff):
             if outputpath is not None:
-                cio.save_topology(os.path.join(outputpath, protein_name(path) + ".top"), rows)
+                cio.save_topology(os.path.join(outputpath, protein_name(path) + ".top"), rows, binary=binary)
             result["files"].append(path)
             if want_counts:
                 result["counts"].append(counts)
