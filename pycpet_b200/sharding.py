@@ -218,11 +218,14 @@ def frames_batch_sharded(compute_batch, n_frames):
         raise ValueError(f"compute_batch returned {len(res)} results for {len(mine)} frames")
     if size == 1:
         return torch.stack(res) if res else torch.zeros(0)
-    shape = tuple(res[0].shape) if res else None
-    shapes = [None] * size
-    _dist().all_gather_object(shapes, shape)
-    shape = next(s for s in shapes if s is not None)
-    dtype = res[0].dtype if res else torch.float32
+    # a rank without frames (fewer frames than ranks) learns shape and dtype from the others
+    meta = (tuple(res[0].shape), res[0].dtype) if res else None
+    metas = [None] * size
+    _dist().all_gather_object(metas, meta)
+    found = [m for m in metas if m is not None]
+    if not found:
+        return torch.zeros(0)
+    shape, dtype = found[0]
     flat = (torch.stack(res).reshape(len(res), -1) if res
             else torch.zeros((0, int(np.prod(shape))), dtype=dtype))
     ids = torch.as_tensor(np.asarray(mine, dtype=np.float64)).reshape(-1, 1).to(flat.device)

@@ -62,13 +62,16 @@ def _worker(rank, size, port, tmp):
     # one call per rank over its frame ids (the shape of Math_ops.topo_hist_frames): int64 counts
     batch = sharding.frames_batch_sharded(
         lambda ids: np.stack([np.full((3, 2), 10 * f, dtype=np.int64) for f in ids]), 7).numpy()
+    # fewer frames than ranks: the idle rank still returns the gathered result with the right dtype
+    lone = sharding.frames_batch_sharded(
+        lambda ids: np.stack([np.full((2, 2), 7 + f, dtype=np.int64) for f in ids]), 1).numpy()
     # exact global order statistics of values spread over the ranks (radix select + all-reduce)
     mine32 = ref_topo[ids][:, 1].astype(np.float32)
     n_all = len(ref_topo)
     stats = sharding.order_stats_sharded(lambda pre, bits: np_radix_hist(mine32, pre, bits),
                                          [0, n_all // 4, n_all // 2, (3 * n_all) // 4, n_all - 1])
     np.savez(os.path.join(tmp, f"r{rank}.npz"), field=full_field, topo=full_topo, counts=counts,
-             frames=frames, batch=batch, ranges=np.array([lo_d, hi_d, lo_c, hi_c]), stats=stats)
+             frames=frames, batch=batch, lone=lone, ranges=np.array([lo_d, hi_d, lo_c, hi_c]), stats=stats)
     dist.destroy_process_group()
 
 
@@ -95,6 +98,7 @@ def test_world_size_2_gloo(tmp_path):
         np.testing.assert_array_equal(z["frames"][:, 0, 0], np.arange(5.0))
         assert z["batch"].dtype == np.int64 and z["batch"].shape == (7, 3, 2)
         np.testing.assert_array_equal(z["batch"][:, 2, 1], 10 * np.arange(7))
+        assert z["lone"].dtype == np.int64 and z["lone"].shape == (1, 2, 2) and np.all(z["lone"] == 7)
         srt = np.sort(topo[:, 1].astype(np.float32))
         n_all = len(srt)
         np.testing.assert_array_equal(z["stats"], srt[[0, n_all // 4, n_all // 2, (3 * n_all) // 4, n_all - 1]])
