@@ -8,6 +8,9 @@ distance x curvature histogram, behind PyCPET's own C-shared-library pattern:
 * ``pycpet_b200.calculator``            mirror of the calculator-level entry points
 * ``pycpet_b200.device.Engine``         device-pointer API (torch tensors in/out, no host copies)
 * ``pycpet_b200.sharding``              one-process-per-GPU partitioning + NCCL gather/all-reduce
+* ``pycpet_b200.md_batch``              MD-trajectory driver: PyCPET's constructor in worker processes,
+                                        pipelined with the batched GPU call
+* ``pycpet_b200.io``                    `.top` / `.dat` writers (np.savetxt's bytes) and readers
 * ``include/cpet_b200.h``               the C ABI itself
 
 There is no CPU / PyTorch fallback: without the built CUDA library and an sm_100 device every
