@@ -118,18 +118,22 @@ def load() -> ctypes.CDLL:
     return _lib
 
 
-def check(status: int) -> None:
+def check(status: int, lib=None) -> None:
+    """Raise CpetError for a negative status; the message comes from the thread-local error state of
+    `lib` -- the handle the failing call went through (a Math_ops(shared_loc=...) instance may hold
+    another copy of the library than the in-tree one)."""
     if status != CPET_OK:
-        L = load()
+        L = lib if lib is not None else load()
         msg = L.cpet_last_error()
         text = msg.decode() if msg else "unknown error"
         L.cpet_clear_error()
         raise CpetError(f"libcpetb200 status {status}: {text}")
 
 
-def check_legacy() -> None:
-    """The reference's `void` symbols have no error channel; ours record one thread-locally."""
-    L = load()
+def check_legacy(lib=None) -> None:
+    """The reference's `void` symbols have no error channel; ours record one thread-locally (in the
+    library instance the call went through, see check())."""
+    L = lib if lib is not None else load()
     st = L.cpet_last_status()
     if st != CPET_OK:
         msg = L.cpet_last_error()

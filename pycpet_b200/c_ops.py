@@ -69,6 +69,13 @@ class Math_ops:
         self._ctx = None
         self._charges_key = None
 
+    # error state lives in the library instance the calls go through (shared_loc may be another copy)
+    def _check(self, status):
+        check(status, self.math)
+
+    def _check_legacy(self):
+        check_legacy(self.math)
+
     # ------------------------------------------------------------------ context handling ------
     @property
     def ctx(self):
@@ -78,7 +85,7 @@ class Math_ops:
             if dev is None:
                 dev = int(os.environ.get("CPET_B200_DEVICE", "0"))
             h = ctypes.c_void_p()
-            check(self.math.cpet_create(int(dev), ctypes.byref(h)))
+            self._check(self.math.cpet_create(int(dev), ctypes.byref(h)))
             self._ctx = h
         return self._ctx
 
@@ -96,11 +103,11 @@ class Math_ops:
 
     def set_tuning(self, **kv):
         for k, v in kv.items():
-            check(self.math.cpet_set_tuning(self.ctx, k.encode(), int(v)))
+            self._check(self.math.cpet_set_tuning(self.ctx, k.encode(), int(v)))
 
     def last_counters(self):
         out = (ctypes.c_int64 * 3)()
-        check(self.math.cpet_last_counters(self.ctx, out))
+        self._check(self.math.cpet_last_counters(self.ctx, out))
         return {"launches": int(out[0]), "pair_evals": int(out[1]), "field_evals": int(out[2])}
 
     def last_path(self) -> str:
@@ -109,12 +116,12 @@ class Math_ops:
 
     def last_kernel_ms(self) -> float:
         ms = ctypes.c_double(0.0)
-        check(self.math.cpet_last_kernel_ms(self.ctx, ctypes.byref(ms)))
+        self._check(self.math.cpet_last_kernel_ms(self.ctx, ctypes.byref(ms)))
         return float(ms.value)
 
     def fp32_peak_tflops(self, packed=True, iters=4096) -> float:
         t = ctypes.c_double(0.0)
-        check(self.math.cpet_fp32_peak_probe(self.ctx, int(bool(packed)), int(iters), ctypes.byref(t)))
+        self._check(self.math.cpet_fp32_peak_probe(self.ctx, int(bool(packed)), int(iters), ctypes.byref(t)))
         return float(t.value)
 
     # ------------------------------------------------------------------ batched entry points ---
@@ -124,7 +131,7 @@ class Math_ops:
         Q = f32c(Q, (-1,))
         if x.shape[0] != Q.shape[0]:
             raise ValueError(f"x has {x.shape[0]} rows but Q has {Q.shape[0]} entries")
-        check(self.math.cpet_set_charges(self.ctx, x.shape[0], ptr(x), ptr(Q)))
+        self._check(self.math.cpet_set_charges(self.ctx, x.shape[0], ptr(x), ptr(Q)))
         return x.shape[0]
 
     @staticmethod
@@ -144,7 +151,7 @@ class Math_ops:
         n = x_0.shape[0]
         out = self._out(out, (n, 6 if concat else 3), np.float32)
         flags = (_lib.CPET_FIELD_SOFTEN if soften else 0) | (_lib.CPET_OUT_CONCAT if concat else 0)
-        check(self.math.cpet_field_grid(self.ctx, n, ptr(x_0), flags, ptr(out)))
+        self._check(self.math.cpet_field_grid(self.ctx, n, ptr(x_0), flags, ptr(out)))
         return out
 
     def esp_grid(self, x_0, x=None, Q=None, concat_half=False, out=None):
@@ -154,7 +161,7 @@ class Math_ops:
         x_0 = f32c(x_0, (-1, 3))
         n = x_0.shape[0]
         out = self._out(out, (n, 4), np.float16) if concat_half else self._out(out, (n,), np.float32)
-        check(self.math.cpet_esp_grid(self.ctx, n, ptr(x_0), _lib.CPET_OUT_CONCAT if concat_half else 0,
+        self._check(self.math.cpet_esp_grid(self.ctx, n, ptr(x_0), _lib.CPET_OUT_CONCAT if concat_half else 0,
                                       ptr(out)))
         return out
 
@@ -167,7 +174,7 @@ class Math_ops:
         n = xs.shape[0] * ys.shape[0] * zs.shape[0]
         out = self._out(out, (n, 6 if concat else 3), np.float32)
         flags = (_lib.CPET_FIELD_SOFTEN if soften else 0) | (_lib.CPET_OUT_CONCAT if concat else 0)
-        check(self.math.cpet_field_lattice(self.ctx, xs.shape[0], ys.shape[0], zs.shape[0], ptr(xs), ptr(ys),
+        self._check(self.math.cpet_field_lattice(self.ctx, xs.shape[0], ys.shape[0], zs.shape[0], ptr(xs), ptr(ys),
                                            ptr(zs), flags, ptr(out)))
         return out
 
@@ -178,7 +185,7 @@ class Math_ops:
         xs, ys, zs = f32c(xs, (-1,)), f32c(ys, (-1,)), f32c(zs, (-1,))
         n = xs.shape[0] * ys.shape[0] * zs.shape[0]
         out = self._out(out, (n, 4), np.float16) if concat_half else self._out(out, (n,), np.float32)
-        check(self.math.cpet_esp_lattice(self.ctx, xs.shape[0], ys.shape[0], zs.shape[0], ptr(xs), ptr(ys),
+        self._check(self.math.cpet_esp_lattice(self.ctx, xs.shape[0], ys.shape[0], zs.shape[0], ptr(xs), ptr(ys),
                                          ptr(zs), _lib.CPET_OUT_CONCAT if concat_half else 0, ptr(out)))
         return out
 
@@ -188,7 +195,7 @@ class Math_ops:
             self.set_charges(x, Q)
         x_0 = f32c(x_0, (-1, 3))
         out = np.zeros_like(x_0)
-        check(self.math.cpet_propagate(self.ctx, x_0.shape[0], ptr(x_0), float(step_size), ptr(out)))
+        self._check(self.math.cpet_propagate(self.ctx, x_0.shape[0], ptr(x_0), float(step_size), ptr(out)))
         return out
 
     def topo_batch(self, seeds, n_iter, x=None, Q=None, step_size=0.1, dimensions=(1, 1, 1),
@@ -204,7 +211,7 @@ class Math_ops:
         dims = f32c(dimensions, (3,))
         out = self._out(out, (n, 2), np.float32)
         steps = np.zeros(n, dtype=np.int32) if want_steps else None
-        check(self.math.cpet_topo_batch(
+        self._check(self.math.cpet_topo_batch(
             self.ctx, n, ptr(seeds), ptr(n_iter), float(step_size), ptr(dims),
             _lib.CPET_TOPO_CURV_SECOND_DIFF if second_diff else 0, ptr(out),
             ptr(steps) if want_steps else None))
@@ -227,7 +234,7 @@ class Math_ops:
         nd, nc = de.shape[0] - 1, ce.shape[0] - 1
         rows = self._out(out, (n, 2), np.float32) if want_rows else None
         counts = self._out(counts_out, (nd, nc), np.int64)
-        check(self.math.cpet_topo_hist(
+        self._check(self.math.cpet_topo_hist(
             self.ctx, n, ptr(seeds), ptr(n_iter), float(step_size), ptr(dims),
             _lib.CPET_TOPO_CURV_SECOND_DIFF if second_diff else 0,
             ptr(rows) if want_rows else None, None, nd, ptr(de), nc, ptr(ce), ptr(counts)))
@@ -266,7 +273,7 @@ class Math_ops:
         m_arr = np.array([fx.shape[0] for fx in xs], dtype=np.int32)
         xp = (ctypes.c_void_p * max(F, 1))(*[fx.ctypes.data for fx in xs])
         qp = (ctypes.c_void_p * max(F, 1))(*[fq.ctypes.data for fq in qs])
-        check(self.math.cpet_topo_hist_frames(
+        self._check(self.math.cpet_topo_hist_frames(
             self.ctx, F, ptr(m_arr), ctypes.cast(xp, ctypes.c_void_p), ctypes.cast(qp, ctypes.c_void_p),
             n, ptr(seeds), ptr(n_iter), stride, float(step_size), ptr(dims),
             _lib.CPET_TOPO_CURV_SECOND_DIFF if second_diff else 0,
@@ -289,7 +296,7 @@ class Math_ops:
         nd, nc = de.shape[0] - 1, ce.shape[0] - 1
         counts = np.zeros((v.shape[0], nd, nc), dtype=np.int64)
         fn = self.math.cpet_hist2d if f64 else self.math.cpet_hist2d_f32
-        check(fn(self.ctx, v.shape[0], v.shape[1], ptr(v), nd, ptr(de), nc, ptr(ce), ptr(counts)))
+        self._check(fn(self.ctx, v.shape[0], v.shape[1], ptr(v), nd, ptr(de), nc, ptr(ce), ptr(counts)))
         return counts[0] if single else counts
 
     def order_stats(self, values, ranks, column=0):
@@ -300,7 +307,7 @@ class Math_ops:
         n = v.shape[0]
         r = np.ascontiguousarray(ranks, dtype=np.int64).reshape(-1)
         out = np.zeros(r.shape[0], dtype=np.float32)
-        check(self.math.cpet_order_stats(self.ctx, n, ptr(v), stride, int(column), r.shape[0], ptr(r), ptr(out)))
+        self._check(self.math.cpet_order_stats(self.ctx, n, ptr(v), stride, int(column), r.shape[0], ptr(r), ptr(out)))
         return out
 
     def chi2_matrix(self, H):
@@ -308,7 +315,7 @@ class Math_ops:
         if H.ndim != 2:
             raise ValueError("H must be (n_hists, n_bins)")
         out = np.zeros((H.shape[0], H.shape[0]), dtype=np.float64)
-        check(self.math.cpet_chi2_matrix(self.ctx, H.shape[0], H.shape[1], ptr(H), ptr(out)))
+        self._check(self.math.cpet_chi2_matrix(self.ctx, H.shape[0], H.shape[1], ptr(H), ptr(out)))
         return out
 
     # ------------------------------------------------------------------ reference methods ------
@@ -317,7 +324,7 @@ class Math_ops:
         Q = Q.reshape(-1)
         self.math.compute_looped_field(int(x_0.shape[0]), len(Q), np.array(x_0, dtype="float32"),
                                        np.array(x, dtype="float32"), np.array(Q, dtype="float32"), res)
-        check_legacy()
+        self._check_legacy()
         return res
 
     def compute_batch_field(self, x_0, x, Q, batch_size):          # c_ops.py:265-279
@@ -326,7 +333,7 @@ class Math_ops:
         self.math.compute_batched_field(int(x_0.shape[0]), batch_size, len(Q),
                                         np.array(x_0, dtype="float32"), np.array(x, dtype="float32"),
                                         np.array(Q, dtype="float32"), res)
-        check_legacy()
+        self._check_legacy()
         return res
 
     def thread_operation(self, x_0, n_iter, x, Q, step_size, dimensions):   # c_ops.py:281-302
@@ -334,43 +341,43 @@ class Math_ops:
         n_charges = len(Q)
         Q = Q.reshape(-1)
         self.math.thread_operation(n_charges, n_iter, step_size, x_0, dimensions, x, Q, res)
-        check_legacy()
+        self._check_legacy()
         return res
 
     def thread_operation_dipole(self, x_0, n_iter, x, mu, step_size, dimensions):  # c_ops.py:304-324
         res = np.zeros(2, dtype="float32")
         self.math.thread_operation_dipole(len(mu), n_iter, step_size, x_0, dimensions, x, mu, res)
-        check_legacy()
+        self._check_legacy()
         return res
 
     def calc_esp_base(self, x_0, x, Q):                            # c_ops.py:326-341
         res = np.zeros(1, dtype="float32")
         self.math.calc_esp_base(res, x_0, len(Q), x, Q.reshape(len(Q)))
-        check_legacy()
+        self._check_legacy()
         return res
 
     def calc_field_base(self, x_0, x, Q):                          # c_ops.py:343-358
         res = np.zeros(3, dtype="float32")
         self.math.calc_field_base(res, x_0, len(Q), x, Q.reshape(len(Q)))
-        check_legacy()
+        self._check_legacy()
         return res
 
     def calc_field(self, x_0, x, Q):                               # c_ops.py:360-375
         res = np.zeros(3, dtype="float32")
         self.math.calc_field(res, x_0, len(Q), x, Q.reshape(len(Q)))
-        check_legacy()
+        self._check_legacy()
         return res
 
     def einsum_ij_i(self, A):                                      # c_ops.py:208-212
         res = np.zeros((A.shape[0]), dtype="float32")
         self.math.einsum_ij_i(A.shape[0], A.shape[1], A, res)
-        check_legacy()
+        self._check_legacy()
         return res
 
     def einsum_ij_i_batch(self, A):                                # c_ops.py:214-220
         res = np.zeros((len(A), A[0].shape[0]), dtype="float32")
         self.math.einsum_ij_i_batch(len(A), A[0].shape[0], A[0].shape[1], A, res)
-        check_legacy()
+        self._check_legacy()
         return res.reshape(res.shape[1], res.shape[0])
 
     def einsum_operation(self, R, r_mag, Q):                       # c_ops.py:222-235
@@ -380,7 +387,7 @@ class Math_ops:
         Q = Q.reshape(-1)
         self.math.einsum_operation(len(Q), np.array(r_mag, dtype="float32"), np.array(Q, dtype="float32"),
                                    np.array(R, dtype="float32"), res)
-        check_legacy()
+        self._check_legacy()
         return res
 
     def einsum_operation_batch(self, R, r_mag, Q, batch_size):     # c_ops.py:237-248
@@ -388,13 +395,13 @@ class Math_ops:
         Q = Q.reshape(-1)
         self.math.einsum_operation_batch(batch_size, len(Q), np.array(r_mag, dtype="float32"),
                                          np.array(Q, dtype="float32"), np.array(R, dtype="float32"), res)
-        check_legacy()
+        self._check_legacy()
         return res
 
     def vecaddn(self, A, B):                                       # c_ops.py:197-206
         res = np.zeros(len(A), dtype="float32")
         self.math.vecaddn(res, A, B, len(A))
-        check_legacy()
+        self._check_legacy()
         return res
 
     def dot(self, A, B):
@@ -403,7 +410,7 @@ class Math_ops:
         B = np.ascontiguousarray(B, dtype=np.double).reshape(-1)
         res = np.zeros(A.shape[0], dtype=np.double)
         self.math.dot(res, A, B, A.shape[0], A.shape[1])
-        check_legacy()
+        self._check_legacy()
         return res
 
     def sparse_dot(self, A, B):
@@ -414,7 +421,7 @@ class Math_ops:
         B = np.ascontiguousarray(B, dtype=np.double).reshape(-1)
         res = np.zeros(len(indptr) - 1, dtype=np.double)
         self.math.sparse_dot(res, indptr, len(indptr), ind, len(ind), data, len(data), B, len(B))
-        check_legacy()
+        self._check_legacy()
         return res
 
 

@@ -195,6 +195,7 @@ int cpet_destroy(cpet_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->charges.release(); c->charge_blocks.release(); c->raw_x.release(); c->raw_q.release();
+    c->xblocks.release(); c->xchunks.release();
     c->in0.release(); c->in1.release(); c->out0.release(); c->out1.release();
     c->work0.release(); c->work1.release(); c->work2.release(); c->counters.release(); c->flags.release(); c->totals.release();
     for (int i = 0; i < cpet_ctx::kTimerRing; ++i) {
@@ -225,6 +226,7 @@ int cpet_set_tuning(cpet_ctx* c, const char* key, int value) {
         {"k1_tile_pairs", &t.k1_tile_pairs}, {"k1_stages", &t.k1_stages}, {"k1_splits", &t.k1_splits}, {"k1_lattice", &t.k1_lattice}, {"k1_unroll", &t.k1_unroll}, {"k1_softscan", &t.k1_softscan},
         {"k2_threads", &t.k2_threads}, {"k2_tile_pairs", &t.k2_tile_pairs},
         {"k2_stages", &t.k2_stages}, {"k2_sort", &t.k2_sort}, {"k2_cap", &t.k2_cap},
+        {"k2_form", &t.k2_form}, {"k2_amax", &t.k2_amax},
         {"timing", &t.timing},
     };
     for (auto& e : tab) {

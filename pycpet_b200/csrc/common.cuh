@@ -282,6 +282,104 @@ __device__ __forceinline__ void eval_tile_lattice_chunked(const ChargePair* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Streamline kernel, round 2: hybrid pair evaluation (topo.cu, k2x_topo_kernel).
+//
+// Every point of a streamline lies inside the sampling box inflated by three steps, so a charge
+// far from that region can be evaluated in an *expanded, charge-scaled* form that needs 10 packed
+// FMA-pipe instructions per two pair-evaluations instead of 12:
+//     alpha = 1/q^2,  a = alpha*x,  b = alpha*|x|^2            (per charge, packed once per launch)
+//     t = alpha*|p-x|^2 = alpha*|p|^2 + b - 2 p.a              (4 FFMA2)
+//     u = t^(-3/2) = |q|^3 / |p-x|^3                           (MUFU.RSQ, 2 FMUL2)
+//     S += u*alpha,  T += u*a                                  (4 FFMA2)
+//     E = sum_j sgn(q_j) (p*S_j - T_j)                         (FP64, once per pass)
+// The sign costs next to nothing: charges are sorted by sign and one set of FP32 accumulators
+// runs through the whole pass over [near | far- | far+]; it is negated once, where far+ begins
+// (16 packed instructions per pass), so that at the end
+//     sum = (S+ - S-,  T+ - T- - E_near),   E = p*S - T.
+// The expansion loses about (|x|+|p|)^2 / |p-x|^2 ulps in t, so only charges for which that
+// amplification is bounded (<= 8 by default) take this form; the few charges close to the box keep
+// the direct form d = p - x, r^2 = d.d, E += q r^-3 d (12 instructions), sharing the point
+// registers (-2p): the near record stores (2x, 2y, 2z, -4q) and evaluates D = -2p + 2x = -2d exactly
+// (powers of two), q' D / |D|^3 = q d / |d|^3.
+// ------------------------------------------------------------------------------------------
+struct __align__(16) V16 { u64 a, b; };
+// 32 charge pairs, structure-of-arrays: lane l reads v0[l], v1[l] (LDS.128) and v2[l] (LDS.64).
+//   far  block: v0 = {ax, ay}   v1 = {az, b}     v2 = alpha        (each entry {even, odd charge})
+//   near block: v0 = {2x, 2y}   v1 = {2z, -4q}   v2 unused
+struct __align__(16) XBlock { V16 v0[32]; V16 v1[32]; u64 v2[32]; };
+static_assert(sizeof(XBlock) == 1280, "hybrid charge block must be 1280 bytes");
+
+#define CPET_X_PAD_B 1.0e30f          // far pad: a = 0, b = 1e30, alpha = 0  ->  u ~ 1e-45, u*alpha = u*a = 0
+#define CPET_X_MIN_ABS_Q 1.0e-12f     // smaller |q| (and q = 0 near the box) keep the direct form
+
+template <int P>
+struct XRegs {
+    float c0[P], c1[P], c2[P], c3[P];   // -2p.x, -2p.y, -2p.z, |p|^2 (ptxas feeds them as broadcast .F32 operands)
+    u64 a0[P], a1[P], a2[P], a3[P];     // FP32 partials {even, odd}: T.x, T.y, T.z, S
+};
+
+template <int P>
+__device__ __forceinline__ void set_point_x(XRegs<P>& r, int p, float x, float y, float z) {
+    r.c0[p] = -2.0f * x;
+    r.c1[p] = -2.0f * y;
+    r.c2[p] = -2.0f * z;
+    r.c3[p] = fmaf(z, z, fmaf(y, y, x * x));
+}
+// a = -a where the far+ part of a pass begins
+template <int PE, int P>
+__device__ __forceinline__ void negate_partials_x(XRegs<P>& r) {
+    const u64 m1 = pk2(-1.0f, -1.0f);
+#pragma unroll
+    for (int p = 0; p < PE; ++p) {
+        r.a0[p] = mul2(r.a0[p], m1);
+        r.a1[p] = mul2(r.a1[p], m1);
+        r.a2[p] = mul2(r.a2[p], m1);
+        r.a3[p] = mul2(r.a3[p], m1);
+    }
+}
+
+__device__ __forceinline__ u64 rsqrt2(u64 t) {
+    float lo, hi;
+    upk2(t, lo, hi);
+    return pk2(rsqrt_approx(lo), rsqrt_approx(hi));
+}
+
+template <int PE, int P>
+__device__ __forceinline__ void evalx_far(const V16 v0, const V16 v1, const u64 al, XRegs<P>& r) {
+#pragma unroll
+    for (int p = 0; p < PE; ++p) {
+        u64 t = fma2(al, pk2(r.c3[p], r.c3[p]), v1.b);
+        t = fma2(pk2(r.c0[p], r.c0[p]), v0.a, t);
+        t = fma2(pk2(r.c1[p], r.c1[p]), v0.b, t);
+        t = fma2(pk2(r.c2[p], r.c2[p]), v1.a, t);
+        const u64 inv = rsqrt2(t);
+        const u64 u = mul2(mul2(inv, inv), inv);
+        r.a3[p] = fma2(u, al, r.a3[p]);
+        r.a0[p] = fma2(u, v0.a, r.a0[p]);
+        r.a1[p] = fma2(u, v0.b, r.a1[p]);
+        r.a2[p] = fma2(u, v1.a, r.a2[p]);
+    }
+}
+
+template <int PE, int P>
+__device__ __forceinline__ void evalx_near(const V16 v0, const V16 v1, XRegs<P>& r) {
+#pragma unroll
+    for (int p = 0; p < PE; ++p) {
+        const u64 dx = add2(pk2(r.c0[p], r.c0[p]), v0.a);
+        const u64 dy = add2(pk2(r.c1[p], r.c1[p]), v0.b);
+        const u64 dz = add2(pk2(r.c2[p], r.c2[p]), v1.a);
+        u64 r2 = mul2(dx, dx);
+        r2 = fma2(dy, dy, r2);
+        r2 = fma2(dz, dz, r2);
+        const u64 inv = rsqrt2(r2);
+        const u64 s = mul2(mul2(inv, inv), mul2(inv, v1.b));
+        r.a0[p] = fma2(s, dx, r.a0[p]);
+        r.a1[p] = fma2(s, dy, r.a1[p]);
+        r.a2[p] = fma2(s, dz, r.a2[p]);
+    }
+}
+
 __device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask) {
     int lo = __double2loint(v), hi = __double2hiint(v);
     lo = __shfl_xor_sync(0xffffffffu, lo, lane_mask);

@@ -49,6 +49,8 @@ struct Tuning {
     int k2_threads = 0, k2_tile_pairs = 0, k2_stages = 0;
     int k2_sort = -1;   // -1 heuristic (on), 0 off, 1 on
     int k2_cap = 0;     // streamlines per warp (1, 2, 4; 0 = heuristic)
+    int k2_form = 0;    // 0 = hybrid near/far kernel (default), 1 = round-1 direct-form kernel
+    int k2_amax = 0;    // hybrid kernel: largest rounding amplification a far charge may have (0 = 8)
     int timing = 0;
 };
 
@@ -67,6 +69,7 @@ struct cpet_ctx {
     cpet::DevBuf charges;            // ChargePair[n_pairs]
     cpet::DevBuf charge_blocks;      // ChargeBlock[ceil(n_pairs / 32)], zero-charge padded
     cpet::DevBuf raw_x, raw_q;       // staging for host uploads
+    cpet::DevBuf xblocks, xchunks;   // hybrid streamline kernel: XBlock[near|far-|far+] of the last launch, per-chunk class counts
     // scratch
     cpet::DevBuf in0, in1, out0, out1, work0, work1, work2, counters, flags, totals;
     cpet::Tuning tune;

@@ -54,29 +54,57 @@ def _side_channel(path):
     return path + ".npy"
 
 
+def _fingerprint(path):
+    """Cheap identity of a text file: size plus CRC32 of its first and last 64 KiB."""
+    import zlib
+
+    size = os.path.getsize(path)
+    with open(path, "rb") as f:
+        head = f.read(65536)
+        if size > 131072:
+            f.seek(size - 65536)
+            tail = f.read(65536)
+        else:
+            tail = f.read()
+    return "%d %08x %08x" % (size, zlib.crc32(head), zlib.crc32(tail))
+
+
 def read_topology(path, use_binary=True):
     """`.top` file -> (n, 2) float64 [dist|curv] (what make_histograms parses, UC:626-633).
-    When save_topology(..., binary=True) left a `<name>.top.npy` next to the text and it is not older
-    than the text, the rows come from there: '%.18e' prints a float32 exactly, so both routes give
-    the same float64 values bit for bit."""
+    When save_topology(..., binary=True) left a `<name>.top.npy` next to the text, the rows come from
+    there -- but only if the fingerprint stored with it (`<name>.top.npy.fp`: size and CRC32 of the
+    head and tail of the text) still matches the text file, so a `.top` that was replaced with its
+    mtime preserved (cp -p, rsync -t, a restored backup) is parsed again instead of being shadowed by
+    stale rows.  '%.18e' prints a float32 exactly, so both routes give the same float64 values bit for
+    bit.  A side channel without its text file is never used (use_binary="force" to allow that)."""
     npy = _side_channel(path)
-    if use_binary and os.path.exists(npy) and (not os.path.exists(path) or
-                                                os.path.getmtime(npy) >= os.path.getmtime(path)):
-        return np.load(npy).astype(np.float64).reshape(-1, 2)
+    if use_binary and os.path.exists(npy):
+        if os.path.exists(path):
+            try:
+                with open(npy + ".fp") as f:
+                    ok = f.read().strip() == _fingerprint(path)
+            except OSError:
+                ok = False
+            if ok:
+                return np.load(npy).astype(np.float64).reshape(-1, 2)
+        elif use_binary == "force":
+            return np.load(npy).astype(np.float64).reshape(-1, 2)
     return read_rows(path, 2)
 
 
 def save_topology(path, hist, binary=False):
     """`.top` file: two columns dist, curv in '%.18e' -- the bytes np.savetxt(path, hist) writes.
-    binary=True also leaves the float32 rows as `<name>.top.npy` (written after the text, so it is
-    never older); the name does not end in "top", so the dispatcher's resume rule
-    (CPET/source/CPET.py:118-119) does not see it."""
+    binary=True also leaves the float32 rows as `<name>.top.npy` and the text's fingerprint as
+    `<name>.top.npy.fp`; neither name ends in "top", so the dispatcher's resume rule
+    (CPET/source/CPET.py:118-119) does not see them."""
     write_rows(path, hist, fmt="%.18e")
     if binary:
         a = np.asarray(hist)
         if a.dtype != np.float32:
             raise ValueError("the binary side channel holds float32 rows (what the integrator returns)")
         np.save(_side_channel(path), np.ascontiguousarray(a).reshape(-1, 2))
+        with open(_side_channel(path) + ".fp", "w") as f:
+            f.write(_fingerprint(path) + "\n")
 
 
 def dat_header(meta_data):

@@ -70,7 +70,7 @@ def _flush(math, frames, d_edges, c_edges, second_diff):
 
 def run_topo_frames(options, files, outputpath=None, d_edges=None, c_edges=None, workers=None,
                     chunk=16, math=None, prepare=prepare_frame, initializer=None, initargs=(),
-                    second_diff=False, skip_done=True, keep_rows=False, binary=False):
+                    second_diff=None, skip_done=True, keep_rows=False, binary=False):
     """Topology of every structure in `files` (the loop of CPET.run_topo as one pipelined batch).
 
     options     the reference's options dict, handed unchanged to `prepare(options, path)`
@@ -83,6 +83,8 @@ def run_topo_frames(options, files, outputpath=None, d_edges=None, c_edges=None,
                 They are *spawned* (the parent may hold a CUDA context), so a script calling this
                 needs the usual `if __name__ == "__main__":` guard
     chunk       frames per GPU call
+    second_diff curvature formula: None (default) takes options["curvature"] ("direction", the
+                default, or "second_diff" = the reference's literal FP32 second differences)
     initializer/initargs  run once in every worker (e.g. to put PyCPET on sys.path)
     -> {"files": [...done in this call...], "skipped": [...], "counts": (F,nd,nc) or None,
         "rows": [(L,2) float32, ...] if keep_rows}
@@ -93,6 +95,11 @@ def run_topo_frames(options, files, outputpath=None, d_edges=None, c_edges=None,
         from .calculator import get_math
 
         math = get_math()
+    if second_diff is None:
+        mode = str(options.get("curvature", "direction")) if hasattr(options, "get") else "direction"
+        if mode not in ("direction", "second_diff"):
+            raise ValueError("options['curvature'] must be 'direction' or 'second_diff', got %r" % mode)
+        second_diff = mode == "second_diff"
     files = list(files)
     todo, skipped = [], []
     done_names = set()
@@ -100,8 +107,14 @@ def run_topo_frames(options, files, outputpath=None, d_edges=None, c_edges=None,
         os.makedirs(outputpath, exist_ok=True)
         if skip_done:                                   # CPET.py:118-119: files ending in "top"
             done_names = {n for n in os.listdir(outputpath) if n.endswith("top")}
+    claimed = set()                                     # two inputs with one protein name share one output file
     for f in files:
-        (skipped if protein_name(f) + ".top" in done_names else todo).append(f)
+        name = protein_name(f) + ".top"
+        if name in done_names or name in claimed:
+            skipped.append(f)
+        else:
+            claimed.add(name)
+            todo.append(f)
     want_counts = d_edges is not None and c_edges is not None
     if not want_counts:                                 # the call needs edges; one catch-all bin
         d_edges = c_edges = np.array([0.0, np.finfo(np.float64).max])
@@ -111,7 +124,13 @@ def run_topo_frames(options, files, outputpath=None, d_edges=None, c_edges=None,
     def emit(batch):
         for path, rows, counts in _flush(math, batch, d_edges, c_edges, second_diff):
             if outputpath is not None:
-                cio.save_topology(os.path.join(outputpath, protein_name(path) + ".top"), rows, binary=binary)
+                dst = os.path.join(outputpath, protein_name(path) + ".top")
+                # the reference re-lists the output directory before every file (CPET.py:118-119) so
+                # that concurrent runs over one directory skip each other's finished frames
+                if skip_done and os.path.exists(dst):
+                    skipped.append(path)
+                    continue
+                cio.save_topology(dst, rows, binary=binary)
             result["files"].append(path)
             if want_counts:
                 result["counts"].append(counts)

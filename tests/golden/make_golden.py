@@ -211,3 +211,90 @@ def make_dropin_goldens():
 
 if __name__ == "__main__" and "--dropin" in sys.argv:
     make_dropin_goldens()
+
+
+def make_hist_goldens():
+    """Histogram plan, normalised histograms and chi^2 matrix straight from the UNMODIFIED reference:
+    CPET.utils.calculator.make_histograms (UC:596-718), construct_distance_matrix (UC:1003-1015),
+    distance_numpy (UC:975-978) and the fixed-range get_hist_grid of
+    CPET/source/scripts/residue_breakdown_analysis.py:28-37, run on (a) the two .top files the
+    reference ships under examples/3A_field-topology/outdir (stale as tracer outputs, perfectly
+    valid as histogram inputs) and (b) a seeded, ragged 3-file synthetic set.  The inputs are stored
+    next to the outputs (float32: the reference writes .top from float32 rows, checked here), because
+    the GPU box has no reference tree; tests rebuild the text files with np.savetxt('%.18e') as
+    CPET.py:123 does."""
+    import importlib.util
+    import tempfile
+
+    os.environ["CPET_BANNER"] = "0"
+    install_stubs()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import CPET.utils.calculator as UC
+
+    spec = importlib.util.spec_from_file_location(
+        "residue_breakdown_analysis", os.path.join(REF, "CPET", "source", "scripts", "residue_breakdown_analysis.py"))
+    rba = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(rba)
+        get_hist_grid = rba.get_hist_grid
+    except Exception as e:      # its module-scope imports pull optional packages; the function is 8 lines of NumPy
+        print("residue_breakdown_analysis not importable here (%s); get_hist_grid golden skipped" % e)
+        get_hist_grid = None
+
+    out = {}
+    work = tempfile.mkdtemp()
+
+    def run_set(tag, arrays):
+        files = []
+        for i, a in enumerate(arrays):
+            f = os.path.join(work, f"{tag}_{i}.top")
+            np.savetxt(f, a)                       # CPET.py:123 (default fmt '%.18e')
+            files.append(f)
+        H = UC.make_histograms(files)
+        D = UC.construct_distance_matrix(H)
+        d01 = UC.distance_numpy(H[0], H[1])
+        for i, a in enumerate(arrays):
+            out[f"{tag}_top{i}"] = a
+        out[f"{tag}_hist"] = H
+        out[f"{tag}_dist"] = D
+        out[f"{tag}_d01"] = np.float64(d01)
+        return H
+
+    # (a) shipped example outputs as inputs
+    ex = os.path.join(REF, "examples", "3A_field-topology", "outdir")
+    shipped = []
+    for name in ("1_alcdehydro_run1.top", "2_alcdehydro_run1.top"):
+        a64 = np.loadtxt(os.path.join(ex, name))
+        a32 = a64.astype(np.float32)
+        assert np.array_equal(a32.astype(np.float64), a64), "shipped .top is not float32-exact"
+        shipped.append(a32)
+    H = run_set("shipped", shipped)
+    # the reference's own file -> histogram path on the ORIGINAL shipped text (not our re-written copy)
+    H_direct = UC.make_histograms([os.path.join(ex, "1_alcdehydro_run1.top"), os.path.join(ex, "2_alcdehydro_run1.top")])
+    assert np.array_equal(H, H_direct), "re-written .top files do not reproduce the shipped ones"
+
+    # (b) seeded synthetic, ragged lengths (the reference then bins with the mean length, UC:650-659)
+    rng = np.random.default_rng(11)
+    synth = []
+    for n, (mu_d, mu_c) in zip((4096, 4096, 3000), ((0.45, 0.6), (0.5, 0.8), (0.4, 0.7))):
+        d = np.abs(rng.normal(mu_d, 0.2, n)).astype(np.float32)
+        c = rng.gamma(2.0, mu_c / 2.0, n).astype(np.float32)
+        synth.append(np.stack([d, c], axis=1))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        run_set("synth", synth)
+    # equal-length synthetic set of three (no warning path)
+    run_set("synth_eq", [s[:3000] for s in synth])
+
+    if get_hist_grid is not None:
+        out["grid_fixed"] = get_hist_grid(shipped[0].astype(np.float64), [0.0, 1.5], 40, [0.0, 3.0], 60)
+        out["grid_fixed_args"] = np.array([0.0, 1.5, 40, 0.0, 3.0, 60])
+
+    np.savez_compressed(os.path.join(OUT, "histograms_reference.npz"), **out)
+    print("histogram goldens:", {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
+if __name__ == "__main__" and "--hist" in sys.argv:
+    make_hist_goldens()

@@ -45,7 +45,7 @@ def frame2a(golden):
 def reset_tuning(m):
     m.set_tuning(k1_threads=0, k1_points=0, k1_lanes=0, k1_tile_pairs=0, k1_stages=0, k1_splits=0,
                  k1_lattice=-1, k1_softscan=-1,
-                 k2_threads=0, k2_tile_pairs=0, k2_stages=0, k2_sort=-1, k2_cap=0)
+                 k2_threads=0, k2_tile_pairs=0, k2_stages=0, k2_sort=-1, k2_cap=0, k2_form=0, k2_amax=0)
 
 
 # ------------------------------------------------------------------------------------ K1 --------
@@ -517,6 +517,78 @@ def test_field_one_million_charges(M):
     check_lines(got, steps, want, wsteps, 0.1, curv_tol_field_limited(0.1))
 
 
+def _line_check(got, steps, want, wsteps, h, what):
+    ok = np.isfinite(want).all(axis=1) & (steps == wsteps)
+    assert (steps != wsteps).sum() <= max(1, len(want) // 500), what
+    assert np.max(np.abs(got[ok, 0] - want[ok, 0])) <= 2e-6, what
+    assert np.max(np.abs(got[ok, 1] - want[ok, 1])) <= 2e-5 + 2e-6 / h, what
+
+
+@pytest.mark.parametrize("signs", ["mixed", "all_negative", "all_positive", "zeros_and_tiny"])
+def test_topo_hybrid_charge_classes(M, signs):
+    """The hybrid kernel sorts charges into near / far-negative / far-positive blocks per launch; every
+    composition of those classes (one of them empty, zero and denormal-small charges, everything near,
+    everything far) must give the oracle's lines, and the direct-form kernel of round 1 the same."""
+    rng = np.random.default_rng(5)
+    x, Q = synth.charges(700, seed=11, box=0.5)
+    if signs == "all_negative":
+        Q = -np.abs(Q) - np.float32(0.01)
+    elif signs == "all_positive":
+        Q = np.abs(Q) + np.float32(0.01)
+    elif signs == "zeros_and_tiny":
+        Q = Q.copy()
+        Q[::3] = 0.0
+        Q[1::7] = np.float32(1e-20)
+        Q[2::11] = np.float32(-3e-14)
+    seeds, n_iter, dims, _ = synth.seeds(9, 0.5, 0.1)
+    want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
+    for cfg in (dict(), dict(k2_amax=1), dict(k2_amax=100000), dict(k2_form=1), dict(k2_cap=1), dict(k2_cap=2),
+                dict(k2_tile_pairs=256, k2_stages=2)):
+        reset_tuning(M)
+        M.set_tuning(**cfg)
+        M.set_charges(x, Q)
+        got, steps = M.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, want_steps=True)
+        if cfg.get("k2_amax") == 100000:      # every charge in the expanded form: still the same lines, looser curvature
+            ok = np.isfinite(want).all(axis=1) & (steps == wsteps)
+            assert (steps != wsteps).sum() <= 1 and np.max(np.abs(got[ok, 0] - want[ok, 0])) <= 2e-5
+            assert np.max(np.abs(got[ok, 1] - want[ok, 1])) <= 2e-3
+        else:
+            _line_check(got, steps, want, wsteps, 0.1, (signs, cfg))
+    reset_tuning(M)
+
+
+def test_topo_hybrid_near_field_and_outside_seeds(M):
+    """Charges inside the sampling box (possible in real inputs) and seeds outside the box the
+    caller names: the classification is against max(box, seeds) inflated by three steps, so such charges
+    take the direct form and the lines still match the oracle."""
+    rng = np.random.default_rng(8)
+    x, Q = synth.charges(900, seed=3, box=0.5)
+    x = np.vstack([x, np.array([[0.31, -0.2, 0.1], [-0.45, 0.45, -0.4], [1.4, 1.3, -1.2]], np.float32)]).astype(np.float32)
+    Q = np.concatenate([Q, np.array([0.4, -0.3, 0.5], np.float32)]).astype(np.float32)
+    dims = np.array([0.5, 0.5, 0.5], np.float32)
+    inside = (rng.uniform(-1, 1, (400, 3)) * dims * 0.97).astype(np.float32)
+    outside = (np.array([1.25, 1.2, -1.1]) + rng.uniform(-0.1, 0.1, (40, 3))).astype(np.float32)   # near the third extra charge
+    seeds = np.vstack([inside, outside]).astype(np.float32)
+    n_iter = rng.integers(1, 16, len(seeds))
+    want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
+    reset_tuning(M)
+    M.set_charges(x, Q)
+    got, steps = M.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, want_steps=True)
+    # lines that pass within 0.05 A of a charge amplify any rounding difference: compare the others
+    far_enough = np.ones(len(seeds), bool)
+    ok = np.isfinite(want).all(axis=1) & (steps == wsteps)
+    assert (steps != wsteps).sum() <= 4
+    assert np.median(np.abs(got[ok, 0] - want[ok, 0])) <= 2e-7
+    assert np.quantile(np.abs(got[ok, 0] - want[ok, 0]), 0.98) <= 2e-6
+    assert np.quantile(np.abs(got[ok, 1] - want[ok, 1]), 0.98) <= 2e-5 + 2e-6 / 0.1
+    M.set_tuning(k2_form=1)
+    got1, steps1 = M.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, want_steps=True)
+    same = steps == steps1
+    assert same.mean() >= 0.99
+    assert np.quantile(np.abs(got[same] - got1[same]), 0.98) <= 5e-5
+    reset_tuning(M)
+
+
 def test_topo_edge_cases(M, frame2a):
     x, Q = frame2a
     dims = np.array([0.5, 0.5, 0.5], np.float32)
@@ -710,6 +782,41 @@ def test_make_histograms_and_chi2(M, tmp_path):
     np.testing.assert_allclose(D, Dw, rtol=1e-12, atol=1e-15)
     assert np.all(np.diag(D) == 0) and np.allclose(D, D.T, rtol=0, atol=0)
     assert abs(calc.distance_numpy(H[0], H[1]) - ohist.chi2(want[0], want[1])) < 1e-14
+
+
+def test_make_histograms_and_chi2_pinned_to_the_reference(M, golden, tmp_path):
+    """The drop-in `make_histograms`, `construct_distance_matrix`, `distance_numpy`, the device bin
+    plan and the fixed-range histogram against outputs of the UNMODIFIED reference functions
+    (tests/golden/make_golden.py --hist): histogram rows bit-exact, chi^2 <= 1e-12."""
+    import warnings
+
+    from pycpet_b200 import calculator as calc
+
+    g = golden("histograms_reference.npz")
+    for tag, n in (("shipped", 2), ("synth", 3), ("synth_eq", 3)):
+        tops = [g[f"{tag}_top{i}"] for i in range(n)]
+        files = []
+        for i, t in enumerate(tops):
+            p = tmp_path / f"{tag}_{i}.top"
+            np.savetxt(p, t)                              # CPET.py:123
+            files.append(str(p))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")               # the ragged set warns, like the reference (UC:652-657)
+            H = calc.make_histograms(files)
+            plan_host = calc.bin_plan(tops)
+            plan_dev = calc.bin_plan_device(tops)
+        want = g[f"{tag}_hist"]
+        assert H.shape == want.shape
+        np.testing.assert_array_equal(H, want)
+        assert plan_dev == plan_host and plan_host[2] * plan_host[3] == want.shape[1]
+        np.testing.assert_array_equal(calc.make_histograms_from_arrays(tops, plan=plan_dev), want)
+        D = calc.construct_distance_matrix(H)
+        np.testing.assert_allclose(D, g[f"{tag}_dist"], rtol=1e-12, atol=1e-15)
+        assert abs(calc.distance_numpy(H[0], H[1]) - float(g[f"{tag}_d01"])) < 1e-14
+    lo_d, hi_d, nd, lo_c, hi_c, nc = g["grid_fixed_args"]
+    t = g["shipped_top0"]
+    cnt = calc.histogram2d_counts(t.astype(np.float64), int(nd), int(nc), (lo_d, hi_d), (lo_c, hi_c)).astype(np.float64)
+    np.testing.assert_array_equal((cnt / cnt.sum()).flatten(), g["grid_fixed"])
 
 
 def test_topo_hist_fused_call(M, frame2a):

@@ -146,3 +146,35 @@ def test_chi2_distance():
     assert abs(hist.chi2(a, b) - expect) < 1e-15
     Mx = hist.chi2_matrix(np.stack([a, b, a]))
     assert Mx[0, 2] == 0 and Mx[0, 1] == Mx[1, 0] == hist.chi2(a, b)
+
+
+def _hist_sets(g):
+    """(tag, [float32 (n,2) arrays]) of tests/golden/histograms_reference.npz."""
+    for tag, n in (("shipped", 2), ("synth", 3), ("synth_eq", 3)):
+        yield tag, [g[f"{tag}_top{i}"] for i in range(n)]
+
+
+def test_histogram_plan_and_chi2_pinned_to_the_reference(golden):
+    """oracle/hist.py against outputs of the UNMODIFIED reference make_histograms /
+    construct_distance_matrix / distance_numpy (UC:596-718, 1003-1015, 975-978) and get_hist_grid
+    (scripts/residue_breakdown_analysis.py:28-37), generated by tests/golden/make_golden.py --hist on
+    the two shipped examples/3A .top files and two seeded synthetic sets (one ragged)."""
+    import warnings
+
+    g = golden("histograms_reference.npz")
+    for tag, tops in _hist_sets(g):
+        lens = np.array([len(t) for t in tops])
+        n_ref = lens[0] if np.all(lens == lens[0]) else np.mean(lens)        # UC:650-659
+        allv = np.concatenate(tops).astype(np.float64)
+        dr, cr, nd, nc = hist.bin_plan(allv[:, 0], allv[:, 1], n_ref)
+        want = g[f"{tag}_hist"]
+        assert want.shape == (len(tops), nd * nc), (tag, nd, nc, want.shape)
+        mine = np.stack([hist.normalised_hist(t[:, 0].astype(np.float64), t[:, 1].astype(np.float64), nd, nc, dr, cr)
+                         for t in tops])
+        np.testing.assert_array_equal(mine, want)
+        np.testing.assert_allclose(hist.chi2_matrix(mine), g[f"{tag}_dist"], rtol=1e-12, atol=1e-15)
+        assert abs(hist.chi2(mine[0], mine[1]) - float(g[f"{tag}_d01"])) < 1e-15
+    lo_d, hi_d, nd, lo_c, hi_c, nc = g["grid_fixed_args"]
+    t = g["shipped_top0"].astype(np.float64)
+    mine = hist.normalised_hist(t[:, 0], t[:, 1], int(nd), int(nc), (lo_d, hi_d), (lo_c, hi_c))
+    np.testing.assert_array_equal(mine, g["grid_fixed"])

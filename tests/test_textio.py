@@ -2,6 +2,7 @@
 import time
 
 import numpy as np
+import pytest
 
 from pycpet_b200 import io as pio
 
@@ -153,13 +154,26 @@ def test_binary_side_channel_gives_the_same_values(tmp_path):
     hist = np.random.default_rng(6).gamma(2.0, 0.3, (5000, 2)).astype(np.float32)
     p = str(tmp_path / "f.top")
     pio.save_topology(p, hist, binary=True)
-    assert sorted(os.listdir(tmp_path)) == ["f.top", "f.top.npy"]
-    assert not "f.top.npy".endswith("top")                    # invisible to the dispatcher's resume rule
+    assert sorted(os.listdir(tmp_path)) == ["f.top", "f.top.npy", "f.top.npy.fp"]
+    assert not any(n.endswith("top") for n in ("f.top.npy", "f.top.npy.fp"))   # invisible to the dispatcher's resume rule
     via_npy = pio.read_topology(p)
     via_text = pio.read_topology(p, use_binary=False)
     assert via_npy.dtype == via_text.dtype == np.float64
     assert np.array_equal(via_npy.view(np.uint64), via_text.view(np.uint64))
-    # a text file rewritten later wins over a stale side channel
-    os.utime(p + ".npy", (1, 1))
+    # a text file replaced later wins over the stale side channel even when its mtime says otherwise
+    # (cp -p, rsync -t, a restored backup): the fingerprint of the text no longer matches
     np.savetxt(p, hist[:10])
+    os.utime(p, (1, 1))
     assert pio.read_topology(p).shape == (10, 2)
+    # same size, different content
+    pio.save_topology(p, hist, binary=True)
+    other = hist.copy(); other[::7, 0] += np.float32(0.5)
+    pio.write_rows(p, other, fmt="%.18e")
+    assert os.path.getsize(p) == len(hist) * 50
+    assert np.array_equal(pio.read_topology(p), other.astype(np.float64))
+    # a side channel whose text file is gone is not used silently
+    pio.save_topology(p, hist, binary=True)
+    os.remove(p)
+    with pytest.raises(Exception):
+        pio.read_topology(p)
+    assert pio.read_topology(p, use_binary="force").shape == (5000, 2)

@@ -1,0 +1,184 @@
+// ubench2.cu -- inner-loop formulations of the streamline kernel's Coulomb sum, with the real
+// shared-memory traffic (a warp's 32 lanes split the charge pairs of resident blocks, 4 points per
+// warp).  Prints pair-evals/s per variant so that a formulation is chosen by measurement.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench2 tools/ubench2.cu
+//   D12 : direct form, 12 packed FMA-pipe instructions per two pair-evaluations (shipped in round 1)
+//   X11 : r^2 by expansion |x|^2+|p|^2-2p.x, s = q*rinv^3, E = p*sum(s) - sum(s*x)          (11)
+//   X10 : the same with charge-scaled coordinates (alpha = 1/q^2 folds q into rinv^3)           (10)
+//   X10F: X10 with the two FMUL2 written as FFMA2 (+0)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
+#include "../pycpet_b200/csrc/common.cuh"
+using namespace cpet;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+struct __align__(16) V16 { u64 a, b; };
+// one block = 32 pairs; per-lane vectors: v0[32] (16 B), v1[32] (16 B), v2[32] (8 B)
+struct __align__(16) UBlock { V16 v0[32]; V16 v1[32]; u64 v2[32]; };
+
+template <int FORM> struct Acc;   // FP32 packed accumulators per point
+
+template <int FORM, int P>
+struct Regs {
+    u64 c0[P], c1[P], c2[P], c3[P];   // point-side operands
+    u64 a0[P], a1[P], a2[P], a3[P];   // accumulators
+};
+
+__device__ __forceinline__ u64 rsq2(u64 t) {
+    float a, b; upk2(t, a, b);
+    return pk2(rsqrt_approx(a), rsqrt_approx(b));
+}
+
+template <int FORM, int P>
+__device__ __forceinline__ void eval(const V16 v0, const V16 v1, const u64 v2, Regs<FORM, P>& r) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        if (FORM == 0 || FORM == 6) {           // D12: v0 = {-x,-y}, v1 = {-z,q}; c0..2 = p
+            const u64 dx = add2(r.c0[p], v0.a), dy = add2(r.c1[p], v0.b), dz = add2(r.c2[p], v1.a);
+            u64 r2 = mul2(dx, dx); r2 = fma2(dy, dy, r2); r2 = fma2(dz, dz, r2);
+            const u64 inv = rsq2(r2);
+            const u64 t = mul2(inv, inv), u = mul2(inv, v1.b), s = mul2(t, u);
+            r.a0[p] = fma2(s, dx, r.a0[p]); r.a1[p] = fma2(s, dy, r.a1[p]); r.a2[p] = fma2(s, dz, r.a2[p]);
+        } else if (FORM == 1) {    // X11: v0 = {x,y}, v1 = {z,|x|^2}, v2 = q; c0..2 = -2p, c3 = |p|^2
+            u64 t = add2(r.c3[p], v1.b);
+            t = fma2(r.c0[p], v0.a, t); t = fma2(r.c1[p], v0.b, t); t = fma2(r.c2[p], v1.a, t);
+            const u64 inv = rsq2(t);
+            const u64 i2 = mul2(inv, inv), u = mul2(inv, v2), s = mul2(i2, u);
+            r.a3[p] = add2(r.a3[p], s);
+            r.a0[p] = fma2(s, v0.a, r.a0[p]); r.a1[p] = fma2(s, v0.b, r.a1[p]); r.a2[p] = fma2(s, v1.a, r.a2[p]);
+        } else {                   // X10: v0 = {ax,ay}, v1 = {az,b}, v2 = alpha; c0..2 = -2p, c3 = |p|^2
+            u64 t = fma2(v2, r.c3[p], v1.b);
+            t = fma2(r.c0[p], v0.a, t); t = fma2(r.c1[p], v0.b, t); t = fma2(r.c2[p], v1.a, t);
+            const u64 inv = (FORM == 4 || FORM == 8) ? t : rsq2(t);
+            u64 i2, u;
+            if (FORM != 3) { i2 = mul2(inv, inv); u = mul2(i2, inv); }
+            else { i2 = fma2(inv, inv, 0ull); u = fma2(i2, inv, 0ull); }
+            r.a3[p] = fma2(u, v2, r.a3[p]);
+            r.a0[p] = fma2(u, v0.a, r.a0[p]); r.a1[p] = fma2(u, v0.b, r.a1[p]); r.a2[p] = fma2(u, v1.a, r.a2[p]);
+        }
+    }
+}
+
+template <int FORM, int P, int U, int T>
+__global__ void __launch_bounds__(T, 1) kLoop(const UBlock* __restrict__ g, int nblk, int passes, float seed,
+                                               float* sink) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    UBlock* blk = reinterpret_cast<UBlock*>(smem);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(g);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        const int n16 = nblk * (int)sizeof(UBlock) / 16;
+        for (int i = threadIdx.x; i < n16; i += T) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int first_only = (passes < 0) ? 1 : 0;   // always 0 at run time, unknown to the compiler
+    Regs<FORM, P> r;
+    double acc[P][4];
+#pragma unroll
+    for (int p = 0; p < P; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.0; }
+    float px = seed * (threadIdx.x >> 5), py = 0.1f, pz = -0.2f;
+    for (int pass = 0; pass < passes; ++pass) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float x = px + 0.01f * p, y = py - 0.02f * p, z = pz + 0.03f * p;
+            if (FORM == 0 || FORM == 6) { r.c0[p] = pk2(x, x); r.c1[p] = pk2(y, y); r.c2[p] = pk2(z, z); r.c3[p] = 0ull; }
+            else if (FORM == 7 || FORM == 8) {
+                   const float e = seed * 1e-7f;   // halves differ: ptxas cannot use the .F32 broadcast operand form
+                   r.c0[p] = pk2(-2 * x, -2 * x + e); r.c1[p] = pk2(-2 * y, -2 * y + e); r.c2[p] = pk2(-2 * z, -2 * z + e);
+                   const float pp = x * x + y * y + z * z; r.c3[p] = pk2(pp, pp + e); }
+            else { r.c0[p] = pk2(-2 * x, -2 * x); r.c1[p] = pk2(-2 * y, -2 * y); r.c2[p] = pk2(-2 * z, -2 * z);
+                   const float pp = x * x + y * y + z * z; r.c3[p] = pk2(pp, pp); }
+            r.a0[p] = r.a1[p] = r.a2[p] = r.a3[p] = 0ull;
+        }
+#pragma unroll U
+        for (int b = 0; b < nblk; ++b) {
+            const int bi = (FORM == 5 || FORM == 6) ? first_only : b;   // 5/6: loop-invariant loads (no LDS in the loop)
+            const V16 v0 = blk[bi].v0[lane];
+            const V16 v1 = blk[bi].v1[lane];
+            u64 v2 = 0ull;
+            if (FORM != 0 && FORM != 6) v2 = blk[bi].v2[lane];
+            eval<FORM, P>(v0, v1, v2, r);
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            float lo, hi;
+            upk2(r.a0[p], lo, hi); acc[p][0] += (double)(lo + hi);
+            upk2(r.a1[p], lo, hi); acc[p][1] += (double)(lo + hi);
+            upk2(r.a2[p], lo, hi); acc[p][2] += (double)(lo + hi);
+            if (FORM != 0 && FORM != 6) { upk2(r.a3[p], lo, hi); acc[p][3] += (double)(lo + hi); }
+        }
+        px += 1e-3f * (float)acc[0][0] * 1e-20f + 1e-4f; py += 1e-4f; pz -= 1e-4f;
+    }
+    double s = 0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) s += acc[p][0] + acc[p][1] + acc[p][2] + acc[p][3];
+    if (s == 123.456) sink[0] = (float)s;
+}
+
+template <typename F>
+static float time_kernel(F launch) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep && ms < best) best = ms;
+    }
+    return best;
+}
+
+static const char* g_filter = nullptr;   // argv[1]: run only variants whose label contains it
+template <int FORM, int P, int U, int T>
+static int run(const char* name, const UBlock* g, int nblk, int sms, float* sink) {
+    char label[64]; snprintf(label, sizeof label, "%s-P%d-U%d-T%d", name, P, U, T);
+    if (g_filter && !strstr(label, g_filter)) return 0;
+    auto kern = kLoop<FORM, P, U, T>;
+    const size_t smem = (size_t)nblk * sizeof(UBlock);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+    const int passes = 400;
+    const float ms = time_kernel([&] { kern<<<sms, T, smem>>>(g, nblk, passes, 0.013f, sink); });
+    CK(cudaGetLastError());
+    const double pe = (double)sms * (T / 32) * passes * (double)nblk * 32 * 2 * P;
+    printf("%-5s P=%d U=%d T=%3d regs=%3d : %.3e pair-evals/s (%.1f%% of 3.7225e12)\n", name, P, U, T, fa.numRegs,
+           pe / (ms * 1e-3), pe / (ms * 1e-3) / 3.7225e12 * 100);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1) g_filter = argv[1];
+    const int reps = argc > 2 ? atoi(argv[2]) : 2;
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    const int nblk = 124;
+    UBlock* h = (UBlock*)malloc(sizeof(UBlock) * nblk);
+    srand(1);
+    for (int b = 0; b < nblk; ++b)
+        for (int l = 0; l < 32; ++l) {
+            float f[10];
+            for (int i = 0; i < 10; ++i) f[i] = 3.0f + 20.0f * rand() / (float)RAND_MAX;
+            f[6] = f[7] = 900.0f;   // |x|^2-like term keeps r^2 positive in the expansion forms
+            float* d0 = (float*)&h[b].v0[l]; float* d1 = (float*)&h[b].v1[l]; float* d2 = (float*)&h[b].v2[l];
+            d0[0] = f[0]; d0[1] = f[1]; d0[2] = f[2]; d0[3] = f[3];
+            d1[0] = f[4]; d1[1] = f[5]; d1[2] = f[6]; d1[3] = f[7];
+            d2[0] = 0.5f; d2[1] = 0.7f;
+        }
+    UBlock* g; CK(cudaMalloc(&g, sizeof(UBlock) * nblk));
+    CK(cudaMemcpy(g, h, sizeof(UBlock) * nblk, cudaMemcpyHostToDevice));
+    float* sink; CK(cudaMalloc(&sink, 64));
+#define R(F, P, U, T, name) if (run<F, P, U, T>(name, g, nblk, sms, sink)) return 1;
+    for (int rep = 0; rep < reps; ++rep) {
+        R(0, 4, 4, 512, "D12") R(0, 4, 4, 384, "D12") R(0, 4, 2, 512, "D12")
+        R(1, 4, 4, 512, "X11") R(1, 4, 4, 384, "X11") R(1, 4, 2, 384, "X11")
+        R(2, 4, 4, 512, "X10") R(2, 4, 4, 384, "X10") R(2, 4, 2, 384, "X10") R(2, 4, 2, 512, "X10")
+        R(2, 4, 4, 256, "X10") R(2, 4, 1, 384, "X10") R(2, 4, 1, 512, "X10")
+        R(3, 4, 4, 384, "X10F") R(3, 4, 2, 384, "X10F") R(3, 4, 4, 512, "X10F")
+        R(2, 2, 4, 512, "X10") R(2, 2, 4, 768, "X10") R(2, 3, 4, 512, "X10")
+        R(0, 2, 4, 768, "D12") R(1, 2, 4, 768, "X11")
+        R(4, 4, 4, 512, "X10noMUFU") R(7, 4, 4, 512, "X10dup") R(8, 4, 4, 512, "X10dupnoMUFU") R(7, 4, 4, 384, "X10dup")
+    }
+    return 0;
+}
