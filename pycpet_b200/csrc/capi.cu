@@ -226,7 +226,7 @@ int cpet_set_tuning(cpet_ctx* c, const char* key, int value) {
         {"k1_tile_pairs", &t.k1_tile_pairs}, {"k1_stages", &t.k1_stages}, {"k1_splits", &t.k1_splits}, {"k1_lattice", &t.k1_lattice}, {"k1_unroll", &t.k1_unroll}, {"k1_softscan", &t.k1_softscan},
         {"k2_threads", &t.k2_threads}, {"k2_tile_pairs", &t.k2_tile_pairs},
         {"k2_stages", &t.k2_stages}, {"k2_sort", &t.k2_sort}, {"k2_cap", &t.k2_cap},
-        {"k2_form", &t.k2_form}, {"k2_amax", &t.k2_amax},
+        {"k2_form", &t.k2_form}, {"k2_amax", &t.k2_amax}, {"k2_unroll", &t.k2_unroll},
         {"timing", &t.timing},
     };
     for (auto& e : tab) {

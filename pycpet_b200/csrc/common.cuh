@@ -288,25 +288,24 @@ __device__ __forceinline__ void eval_tile_lattice_chunked(const ChargePair* __re
 // Every point of a streamline lies inside the sampling box inflated by three steps, so a charge
 // far from that region can be evaluated in an *expanded, charge-scaled* form that needs 10 packed
 // FMA-pipe instructions per two pair-evaluations instead of 12:
-//     alpha = 1/q^2,  a = alpha*x,  b = alpha*|x|^2            (per charge, packed once per launch)
-//     t = alpha*|p-x|^2 = alpha*|p|^2 + b - 2 p.a              (4 FFMA2)
-//     u = t^(-3/2) = |q|^3 / |p-x|^3                           (MUFU.RSQ, 2 FMUL2)
-//     S += u*alpha,  T += u*a                                  (4 FFMA2)
-//     E = sum_j sgn(q_j) (p*S_j - T_j)                         (FP64, once per pass)
-// The sign costs next to nothing: charges are sorted by sign and one set of FP32 accumulators
-// runs through the whole pass over [near | far- | far+]; it is negated once, where far+ begins
-// (16 packed instructions per pass), so that at the end
-//     sum = (S+ - S-,  T+ - T- - E_near),   E = p*S - T.
+//     alpha = s/q^2,  a = alpha*x,  b = alpha*|x|^2,  s = sgn(q)   (per charge, packed once per launch)
+//     t = alpha*|p-x|^2 = alpha*|p|^2 + b - 2 p.a                  (4 FFMA2; t carries the sign of q)
+//     u = |t|^(-3/2) = |q|^3 / |p-x|^3                             (MUFU.RSQ of |t| -- the absolute value is
+//                                                                   an operand modifier --, 2 FMUL2)
+//     S += u*alpha,  T += u*a                                      (4 FFMA2: sums of q/r^3 and q x/r^3)
+//     E = p*S - T                                                  (FP64, once per pass)
+// The sign of the charge rides on the whole record, so negative and positive charges run through
+// the same loop and the same accumulators.
 // The expansion loses about (|x|+|p|)^2 / |p-x|^2 ulps in t, so only charges for which that
 // amplification is bounded (<= 8 by default) take this form; the few charges close to the box keep
 // the direct form d = p - x, r^2 = d.d, E += q r^-3 d (12 instructions), sharing the point
-// registers (-2p): the near record stores (2x, 2y, 2z, -4q) and evaluates D = -2p + 2x = -2d exactly
-// (powers of two), q' D / |D|^3 = q d / |d|^3.
+// registers (-2p): the near record stores (2x, 2y, 2z, 4q) and evaluates D = -2p + 2x = -2d exactly
+// (powers of two), q' D / |D|^3 = -q d / |d|^3, i.e. the near field enters T negatively.
 // ------------------------------------------------------------------------------------------
 struct __align__(16) V16 { u64 a, b; };
 // 32 charge pairs, structure-of-arrays: lane l reads v0[l], v1[l] (LDS.128) and v2[l] (LDS.64).
-//   far  block: v0 = {ax, ay}   v1 = {az, b}     v2 = alpha        (each entry {even, odd charge})
-//   near block: v0 = {2x, 2y}   v1 = {2z, -4q}   v2 unused
+//   far  block: v0 = {ax, ay}   v1 = {az, b}    v2 = alpha        (each entry {even, odd charge})
+//   near block: v0 = {2x, 2y}   v1 = {2z, 4q}   v2 unused
 struct __align__(16) XBlock { V16 v0[32]; V16 v1[32]; u64 v2[32]; };
 static_assert(sizeof(XBlock) == 1280, "hybrid charge block must be 1280 bytes");
 
@@ -316,7 +315,7 @@ static_assert(sizeof(XBlock) == 1280, "hybrid charge block must be 1280 bytes");
 template <int P>
 struct XRegs {
     float c0[P], c1[P], c2[P], c3[P];   // -2p.x, -2p.y, -2p.z, |p|^2 (ptxas feeds them as broadcast .F32 operands)
-    u64 a0[P], a1[P], a2[P], a3[P];     // FP32 partials {even, odd}: T.x, T.y, T.z, S
+    u64 a0[P], a1[P], a2[P], a3[P];     // FP32 partials {even, odd}: T.x - E_near.x, T.y - .., T.z - .., S
 };
 
 template <int P>
@@ -326,23 +325,15 @@ __device__ __forceinline__ void set_point_x(XRegs<P>& r, int p, float x, float y
     r.c2[p] = -2.0f * z;
     r.c3[p] = fmaf(z, z, fmaf(y, y, x * x));
 }
-// a = -a where the far+ part of a pass begins
-template <int PE, int P>
-__device__ __forceinline__ void negate_partials_x(XRegs<P>& r) {
-    const u64 m1 = pk2(-1.0f, -1.0f);
-#pragma unroll
-    for (int p = 0; p < PE; ++p) {
-        r.a0[p] = mul2(r.a0[p], m1);
-        r.a1[p] = mul2(r.a1[p], m1);
-        r.a2[p] = mul2(r.a2[p], m1);
-        r.a3[p] = mul2(r.a3[p], m1);
-    }
-}
-
 __device__ __forceinline__ u64 rsqrt2(u64 t) {
     float lo, hi;
     upk2(t, lo, hi);
     return pk2(rsqrt_approx(lo), rsqrt_approx(hi));
+}
+__device__ __forceinline__ u64 rsqrt2_abs(u64 t) {       // MUFU.RSQ |x|: the sign of the charge rides on t
+    float lo, hi;
+    upk2(t, lo, hi);
+    return pk2(rsqrt_approx(fabsf(lo)), rsqrt_approx(fabsf(hi)));
 }
 
 template <int PE, int P>
@@ -353,7 +344,7 @@ __device__ __forceinline__ void evalx_far(const V16 v0, const V16 v1, const u64 
         t = fma2(pk2(r.c0[p], r.c0[p]), v0.a, t);
         t = fma2(pk2(r.c1[p], r.c1[p]), v0.b, t);
         t = fma2(pk2(r.c2[p], r.c2[p]), v1.a, t);
-        const u64 inv = rsqrt2(t);
+        const u64 inv = rsqrt2_abs(t);
         const u64 u = mul2(mul2(inv, inv), inv);
         r.a3[p] = fma2(u, al, r.a3[p]);
         r.a0[p] = fma2(u, v0.a, r.a0[p]);

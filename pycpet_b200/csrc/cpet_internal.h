@@ -50,6 +50,7 @@ struct Tuning {
     int k2_sort = -1;   // -1 heuristic (on), 0 off, 1 on
     int k2_cap = 0;     // streamlines per warp (1, 2, 4; 0 = heuristic)
     int k2_form = 0;    // 0 = hybrid near/far kernel (default), 1 = round-1 direct-form kernel
+    int k2_unroll = 0;  // hybrid kernel: far-loop unroll of the 4-point pass (3, 4 or 6; 0 = 3)
     int k2_amax = 0;    // hybrid kernel: largest rounding amplification a far charge may have (0 = 8)
     int timing = 0;
 };

@@ -431,15 +431,15 @@ __global__ void __launch_bounds__(CPET_K2_MAXT, 1) k2w_topo_kernel(const K2WPara
 // the arithmetic of the charge loop (common.cuh: evalx_far / evalx_near) and, because that needs the
 // charges classified against the sampling box, a per-launch packing step:
 //   k2x_extent_kernel   max |seed| per axis (seeds may lie outside the box the caller names)
-//   k2x_count_kernel    class of every charge (near / far negative / far positive), counts per chunk
-//   k2x_scatter_kernel  stable compaction into XBlocks [near | far- | far+], zero-weight padding
+//   k2x_count_kernel    class of every charge (near / far), counts per chunk
+//   k2x_scatter_kernel  stable compaction into XBlocks [near | far], zero-weight padding
 // All three are O(M + L) and run on the launch stream; nothing is read back by the host (the
 // integrator takes the block counts from device memory).
 // =============================================================================================
 struct K2XMeta {
     unsigned ext[3];                 // max |seed coordinate| per axis, float bits
-    int n_near, n_neg, n_pos;        // charges per class
-    int nb_near, nb_neg, nb_pos;     // blocks per class, in array order
+    int n_near, n_far;               // charges per class
+    int nb_near, nb_far;             // blocks per class, in array order
     int nb_total;
 };
 
@@ -475,7 +475,7 @@ __device__ __forceinline__ K2XBox k2x_box(const K2XMeta* meta, float dx, float d
     return b;
 }
 
-// 0 = near (direct form), 1 = far, q < 0, 2 = far, q >= 0.  A charge is far when the rounding
+// 0 = near (direct form), 1 = far (expanded form).  A charge is far when the rounding
 // amplification of the expanded r^2, (|x| + |p|max)^2 / dist(x, region)^2, is at most amax.
 __device__ __forceinline__ int k2x_class(float x, float y, float z, float q, const K2XBox& b) {
     const float ex = fmaxf(fabsf(x) - b.bx, 0.f), ey = fmaxf(fabsf(y) - b.by, 0.f), ez = fmaxf(fabsf(z) - b.bz, 0.f);
@@ -483,9 +483,9 @@ __device__ __forceinline__ int k2x_class(float x, float y, float z, float q, con
     const float xn = sqrtf(x * x + y * y + z * z) + b.pmax;
     const bool far = (xn * xn <= b.amax * r2min) && (xn < 1.0e6f);      // false for NaN
     if (!far) return 0;
-    if (q == 0.f) return 2;                                            // zero-weight far record
+    if (q == 0.f) return 1;                                            // zero-weight far record
     if (!(fabsf(q) >= CPET_X_MIN_ABS_Q)) return 0;                     // tiny or NaN charge
-    return q < 0.f ? 1 : 2;
+    return 1;
 }
 
 __device__ __forceinline__ void k2x_load_charge(const ChargePair* __restrict__ pairs, int i, float& x, float& y,
@@ -499,8 +499,8 @@ __global__ void __launch_bounds__(K2X_CHUNK) k2x_count_kernel(const ChargePair* 
                                                               float dx, float dy, float dz, float h, float amax,
                                                               const K2XMeta* __restrict__ meta,
                                                               int* __restrict__ chunk_counts) {
-    __shared__ int cnt[3];
-    if (threadIdx.x < 3) cnt[threadIdx.x] = 0;
+    __shared__ int cnt[2];
+    if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
     __syncthreads();
     const K2XBox box = k2x_box(meta, dx, dy, dz, h, amax);
     const int i = blockIdx.x * K2X_CHUNK + threadIdx.x;
@@ -511,12 +511,12 @@ __global__ void __launch_bounds__(K2X_CHUNK) k2x_count_kernel(const ChargePair* 
         cls = k2x_class(x, y, z, q, box);
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 2; ++k) {
         const unsigned bal = __ballot_sync(0xffffffffu, cls == k);
         if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&cnt[k], __popc(bal));
     }
     __syncthreads();
-    if (threadIdx.x < 3) chunk_counts[4 * blockIdx.x + threadIdx.x] = cnt[threadIdx.x];
+    if (threadIdx.x < 2) chunk_counts[2 * blockIdx.x + threadIdx.x] = cnt[threadIdx.x];
 }
 
 __device__ __forceinline__ void k2x_store(XBlock* __restrict__ out, int block, int slot, float f0, float f1,
@@ -532,11 +532,11 @@ __device__ __forceinline__ void k2x_store_class(XBlock* __restrict__ out, int cl
     const int block = first_block + (slot >> 6);
     if (cls == 0) {
         if (pad) k2x_store(out, block, slot, 2.0f * CPET_PAD_COORD, 2.0f * CPET_PAD_COORD, 2.0f * CPET_PAD_COORD, 0.f, 0.f);
-        else k2x_store(out, block, slot, 2.0f * x, 2.0f * y, 2.0f * z, -4.0f * q, 0.f);
+        else k2x_store(out, block, slot, 2.0f * x, 2.0f * y, 2.0f * z, 4.0f * q, 0.f);
     } else if (pad || q == 0.f) {
         k2x_store(out, block, slot, 0.f, 0.f, 0.f, CPET_X_PAD_B, 0.f);
     } else {
-        const double al = 1.0 / ((double)q * (double)q);
+        const double al = (q < 0.f ? -1.0 : 1.0) / ((double)q * (double)q);   // the record carries the sign of q
         const double x2 = (double)x * x + (double)y * y + (double)z * z;
         k2x_store(out, block, slot, (float)(al * x), (float)(al * y), (float)(al * z), (float)(al * x2), (float)al);
     }
@@ -547,22 +547,22 @@ __global__ void __launch_bounds__(K2X_CHUNK) k2x_scatter_kernel(const ChargePair
                                                                 K2XMeta* __restrict__ meta,
                                                                 const int* __restrict__ chunk_counts, int n_chunks,
                                                                 XBlock* __restrict__ out) {
-    __shared__ int s_red[32][6];
-    __shared__ int s_pre[3], s_tot[3];
-    __shared__ int s_warp[32][3];
+    __shared__ int s_red[32][4];
+    __shared__ int s_pre[2], s_tot[2];
+    __shared__ int s_warp[32][2];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     // charges of each class in the chunks before this one, and in all chunks
-    int v[6] = {0, 0, 0, 0, 0, 0};
+    int v[4] = {0, 0, 0, 0};
     for (int c = tid; c < n_chunks; c += K2X_CHUNK) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int n = chunk_counts[4 * c + k];
-            v[3 + k] += n;
+        for (int k = 0; k < 2; ++k) {
+            const int n = chunk_counts[2 * c + k];
+            v[2 + k] += n;
             if (c < (int)blockIdx.x) v[k] += n;
         }
     }
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 4; ++k) {
         v[k] = __reduce_add_sync(0xffffffffu, v[k]);
         if (lane == 0) s_red[w][k] = v[k];
     }
@@ -576,38 +576,38 @@ __global__ void __launch_bounds__(K2X_CHUNK) k2x_scatter_kernel(const ChargePair
     }
     int rank = 0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 2; ++k) {
         const unsigned bal = __ballot_sync(0xffffffffu, cls == k);
         if (cls == k) rank = __popc(bal & ((1u << lane) - 1u));
         if (lane == 0) s_warp[w][k] = __popc(bal);
     }
     __syncthreads();
-    if (tid < 6) {
+    if (tid < 4) {
         int t = 0;
         for (int j = 0; j < 32; ++j) t += s_red[j][tid];
-        if (tid < 3) s_pre[tid] = t; else s_tot[tid - 3] = t;
+        if (tid < 2) s_pre[tid] = t; else s_tot[tid - 2] = t;
     }
-    if (tid >= 32 && tid < 35) {          // exclusive scan of the per-warp counts of class tid-32
+    if (tid >= 32 && tid < 34) {          // exclusive scan of the per-warp counts of class tid-32
         const int k = tid - 32;
         int run = 0;
         for (int j = 0; j < 32; ++j) { const int n = s_warp[j][k]; s_warp[j][k] = run; run += n; }
     }
     __syncthreads();
-    const int nb0 = (s_tot[0] + 63) >> 6, nb1 = (s_tot[1] + 63) >> 6, nb2 = (s_tot[2] + 63) >> 6;
-    const int first[3] = {0, nb0, nb0 + nb1};
+    const int nb0 = (s_tot[0] + 63) >> 6, nb1 = (s_tot[1] + 63) >> 6;
+    const int first[2] = {0, nb0};
     if (cls >= 0) k2x_store_class(out, cls, first[cls], s_pre[cls] + s_warp[w][cls] + rank, x, y, z, q, false);
     if (blockIdx.x == 0) {
         // zero-weight padding up to a whole block per class, and the counts the integrator reads
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int nb = k == 0 ? nb0 : (k == 1 ? nb1 : nb2);
+        for (int k = 0; k < 2; ++k) {
+            const int nb = k == 0 ? nb0 : nb1;
             for (int slot = s_tot[k] + tid; slot < nb * 64; slot += K2X_CHUNK)
                 k2x_store_class(out, k, first[k], slot, 0.f, 0.f, 0.f, 0.f, true);
         }
         if (tid == 0) {
-            meta->n_near = s_tot[0]; meta->n_neg = s_tot[1]; meta->n_pos = s_tot[2];
-            meta->nb_near = nb0; meta->nb_neg = nb1; meta->nb_pos = nb2;
-            meta->nb_total = nb0 + nb1 + nb2;
+            meta->n_near = s_tot[0]; meta->n_far = s_tot[1];
+            meta->nb_near = nb0; meta->nb_far = nb1;
+            meta->nb_total = nb0 + nb1;
         }
     }
 }
@@ -635,7 +635,7 @@ struct __align__(16) WarpLinesX {
     float px[4], py[4], pz[4];         // current point p_k
     float sx[4], sy[4], sz[4];         // seed
     float ux[4], uy[4], uz[4];         // unit field direction at p_{k-1}
-    double tx[4], ty[4], tz[4], ts[4]; // sums of the current pass: T - E_near (3) and S
+    double tx[4], ty[4], tz[4], ts[4]; // sums of the current pass: T - E_near (3) and S (signed by the charges)
     float dist[4], kinit[4];
     int line[4], n_it[4], k[4], k_end[4];
     float m1x[4], m1y[4], m1z[4], m2x[4], m2y[4], m2z[4];   // p_{k-1}, p_{k-2} (second-difference mode)
@@ -722,21 +722,10 @@ __device__ __forceinline__ void evalx_run(const unsigned char* __restrict__ p16,
     }
 }
 
-// [near | far-] sums enter the totals negatively: negate what has been accumulated where far+ begins
-template <int PE>
-__device__ __forceinline__ void flip_sums(XRegs<4>& r, double (&v)[4], bool& flipped) {
-    negate_partials_x<PE, 4>(r);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) v[c] = -v[c];
-    flipped = true;
-}
-
-// Blocks [g0, g1) of the array [near | far- | far+] (tile[0] is block gbase) against the warp's PE
-// points; `flipped` says whether the sums have already been negated for the far+ part.
+// Blocks [g0, g1) of the array [near | far] (tile[0] is block gbase) against the warp's PE points.
 template <int PE, int U>
 __device__ __forceinline__ void evalx_blocks(const XBlock* __restrict__ tile, int gbase, int g0, int g1,
-                                             int nb_near, int nb_neg_end, int lane, XRegs<4>& r,
-                                             double (&v)[4], int& run, bool& flipped) {
+                                             int nb_near, int lane, XRegs<4>& r, double (&v)[4], int& run) {
     const unsigned char* base = reinterpret_cast<const unsigned char*>(tile) - (size_t)gbase * sizeof(XBlock);
     const unsigned char* l16 = base + 16 * lane;
     const unsigned char* l8 = base + 1024 + 8 * lane;
@@ -746,21 +735,12 @@ __device__ __forceinline__ void evalx_blocks(const XBlock* __restrict__ tile, in
         evalx_run<PE, 1, true>(l16 + (size_t)b * sizeof(XBlock), l8, e - b, lane, r, v, run);
         b = e;
     }
-    if (b < nb_neg_end && b < g1) {
-        const int e = min(g1, nb_neg_end);
-        evalx_run<PE, U, false>(l16 + (size_t)b * sizeof(XBlock), l8 + (size_t)b * sizeof(XBlock), e - b, lane, r, v, run);
-        b = e;
-    }
-    if (b < g1) {
-        if (!flipped) flip_sums<PE>(r, v, flipped);
+    if (b < g1)
         evalx_run<PE, U, false>(l16 + (size_t)b * sizeof(XBlock), l8 + (size_t)b * sizeof(XBlock), g1 - b, lane, r, v, run);
-    }
 }
 
-// end of a pass: a frame without far+ blocks never met the sign flip
 template <int PE>
-__device__ __forceinline__ void finish_pass(XRegs<4>& r, double (&v)[4], int lane, bool flipped) {
-    if (!flipped) flip_sums<PE>(r, v, flipped);
+__device__ __forceinline__ void finish_pass(XRegs<4>& r, double (&v)[4], int lane) {
     fold_exchange<PE>(r, v, lane);
     finish_exchange<PE>(v);
 }
@@ -781,7 +761,6 @@ __global__ void __launch_bounds__(CPET_K2X_MAXT, 1) k2x_topo_kernel(const K2XPar
     const int TB = prm.tile_blocks;
     const int nb_total = prm.meta->nb_total;
     const int nb_near = prm.meta->nb_near;
-    const int nb_neg_end = nb_near + prm.meta->nb_neg;
     const int NT = (nb_total + TB - 1) / TB;
 
     if (tid == 0) {
@@ -884,26 +863,25 @@ __global__ void __launch_bounds__(CPET_K2X_MAXT, 1) k2x_topo_kernel(const K2XPar
 
         // ---- field sums at those points: all charges, split over the 32 lanes -------------------------
         int run = 0;
-        bool flipped = false;
         if (prm.resident) {
-            if (na > 2) { evalx_blocks<4, U4>(ring, 0, 0, nb_total, nb_near, nb_neg_end, lane, r, v, run, flipped); finish_pass<4>(r, v, lane, flipped); }
-            else if (na == 2) { evalx_blocks<2, U2>(ring, 0, 0, nb_total, nb_near, nb_neg_end, lane, r, v, run, flipped); finish_pass<2>(r, v, lane, flipped); }
-            else { evalx_blocks<1, 8>(ring, 0, 0, nb_total, nb_near, nb_neg_end, lane, r, v, run, flipped); finish_pass<1>(r, v, lane, flipped); }
+            if (na > 2) { evalx_blocks<4, U4>(ring, 0, 0, nb_total, nb_near, lane, r, v, run); finish_pass<4>(r, v, lane); }
+            else if (na == 2) { evalx_blocks<2, U2>(ring, 0, 0, nb_total, nb_near, lane, r, v, run); finish_pass<2>(r, v, lane); }
+            else { evalx_blocks<1, 8>(ring, 0, 0, nb_total, nb_near, lane, r, v, run); finish_pass<1>(r, v, lane); }
         } else {
             for (int t = 0; t < NT; ++t, ++it) {
                 const int stage = it % S;
                 mbar_wait(&full[stage], (uint32_t)((it / S) & 1));
                 const int g0 = t * TB, g1 = min(nb_total, g0 + TB);
                 const XBlock* tile = ring + (size_t)stage * TB;
-                if (na > 2) evalx_blocks<4, U4>(tile, g0, g0, g1, nb_near, nb_neg_end, lane, r, v, run, flipped);
-                else if (na == 2) evalx_blocks<2, U2>(tile, g0, g0, g1, nb_near, nb_neg_end, lane, r, v, run, flipped);
-                else if (na == 1) evalx_blocks<1, 8>(tile, g0, g0, g1, nb_near, nb_neg_end, lane, r, v, run, flipped);
+                if (na > 2) evalx_blocks<4, U4>(tile, g0, g0, g1, nb_near, lane, r, v, run);
+                else if (na == 2) evalx_blocks<2, U2>(tile, g0, g0, g1, nb_near, lane, r, v, run);
+                else if (na == 1) evalx_blocks<1, 8>(tile, g0, g0, g1, nb_near, lane, r, v, run);
                 __syncthreads();                      // stage fully consumed by the CTA
                 if (tid == 0) { issue(issued); ++issued; }   // speculative: next pass's tiles too
             }
-            if (na > 2) finish_pass<4>(r, v, lane, flipped);
-            else if (na == 2) finish_pass<2>(r, v, lane, flipped);
-            else finish_pass<1>(r, v, lane, flipped);
+            if (na > 2) finish_pass<4>(r, v, lane);
+            else if (na == 2) finish_pass<2>(r, v, lane);
+            else finish_pass<1>(r, v, lane);
         }
 
         // ---- the totals of position p go to line slot src[p] ---------------------------------------------
@@ -1227,7 +1205,7 @@ static int launch_topo_hybrid(cpet_ctx* c, int n_lines, const float* d_seeds, co
 
     // --- charge staging plan; the class sizes are only known on the device, so plan for the worst
     //     case: every class ends in a partly filled block
-    const int max_blocks = (c->n_charges + 63) / 64 + 3;
+    const int max_blocks = (c->n_charges + 63) / 64 + 2;
     K2XParams prm;
     size_t smem;
     if (hdr + (size_t)max_blocks * sizeof(XBlock) <= (size_t)c->max_smem_optin && tu.k2_stages <= 0 &&
@@ -1266,7 +1244,7 @@ static int launch_topo_hybrid(cpet_ctx* c, int n_lines, const float* d_seeds, co
     static_assert(sizeof(K2XMeta) <= 48, "K2XMeta must fit the counter block header");
     const int n_chunks = (c->n_charges + K2X_CHUNK - 1) / K2X_CHUNK;
     if (int rc = c->xblocks.reserve(sizeof(XBlock) * (size_t)max_blocks)) return rc;
-    if (int rc = c->xchunks.reserve(sizeof(int) * 4 * (size_t)(n_chunks > 0 ? n_chunks : 1))) return rc;
+    if (int rc = c->xchunks.reserve(sizeof(int) * 2 * (size_t)(n_chunks > 0 ? n_chunks : 1))) return rc;
     const float amax = tu.k2_amax > 0 ? (float)tu.k2_amax : 8.0f;
     {
         int eb = (n_lines + 255) / 256;
@@ -1298,8 +1276,16 @@ static int launch_topo_hybrid(cpet_ctx* c, int n_lines, const float* d_seeds, co
 
     KernelTimer timer(c);   // brackets the integrator kernel only (the roofline's "dominant kernel")
     const bool sd = (flags & CPET_TOPO_CURV_SECOND_DIFF) != 0u;
-    const int rc = sd ? launch_k2x_inst<true, 4, 4>(c, prm, grid, threads, smem)
-                      : launch_k2x_inst<false, 4, 4>(c, prm, grid, threads, smem);
+    // far-loop unroll of the 4-point pass (k2_unroll; default by staging mode, see profiles/round2_k2x.md)
+    int rc;
+    const int unroll = tu.k2_unroll > 0 ? tu.k2_unroll : (prm.resident && c->n_charges >= 4000 ? 6 : 4);
+#define K2X_LAUNCH(U) (sd ? launch_k2x_inst<true, U, 4>(c, prm, grid, threads, smem) : launch_k2x_inst<false, U, 4>(c, prm, grid, threads, smem))
+    if (unroll <= 3) rc = K2X_LAUNCH(3);
+    else if (unroll <= 4) rc = K2X_LAUNCH(4);
+    else if (unroll <= 6) rc = K2X_LAUNCH(6);
+    else if (unroll <= 8) rc = K2X_LAUNCH(8);
+    else rc = K2X_LAUNCH(12);
+#undef K2X_LAUNCH
     if (rc) return rc;
     launches += 1;
     c->last_counters[0] = launches;

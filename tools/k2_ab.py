@@ -33,7 +33,7 @@ def main():
         ref, _ = f64.topo_batch(seeds[sample], n_iter[sample], x, Q, h, dims)
         outs = {}
         for cfg in [dict(k2_form=1), dict(k2_form=0)] + extra:
-            eng.set_tuning(k2_form=0, k2_threads=0, k2_cap=0, k2_amax=0)
+            eng.set_tuning(k2_form=0, k2_threads=0, k2_cap=0, k2_amax=0, k2_unroll=0)
             eng.set_tuning(**cfg)
             best = 1e30
             for _ in range(5):
