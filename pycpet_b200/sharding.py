@@ -43,24 +43,22 @@ def frames_for_rank(n_frames: int, rank: int, size: int):
     return list(range(rank, int(n_frames), size))
 
 
-def deal_lines(n_iter, rank: int, size: int, block: int = 32):
-    """Line ids of this rank for a single-frame topology: lines sorted by n_iter (descending,
-    stable) and dealt round-robin in warp-sized blocks, so every rank gets the same mix of long
-    and short lines (cost is proportional to the steps taken)."""
+def deal_lines_all(n_iter, size: int, block: int = 32):
+    """Line ids of every rank for a single-frame topology: lines sorted by n_iter (descending,
+    stable) and dealt in warp-sized blocks in serpentine order, so every rank gets the same mix of
+    long and short lines (cost is proportional to the steps taken).  Deterministic in (n_iter, size):
+    every rank can name every other rank's lines, so no ids travel with the results."""
     n_iter = np.asarray(n_iter).reshape(-1)
     order = np.argsort(-n_iter, kind="stable")
-    nblk = (len(order) + block - 1) // block
-    mine = []
-    for b in range(nblk):
-        rnd, pos = divmod(b, size)
-        owner = pos if (rnd % 2 == 0) else size - 1 - pos      # serpentine: cancels the sort bias
-        if owner == rank:
-            mine.append(order[b * block:(b + 1) * block])
-    return np.concatenate(mine) if mine else np.zeros(0, dtype=np.int64)
+    blk = np.arange(len(order)) // block
+    rnd, pos = np.divmod(blk, size)
+    owner = np.where(rnd % 2 == 0, pos, size - 1 - pos)          # serpentine: cancels the sort bias
+    return [order[owner == r] for r in range(size)]
 
 
-def _device_of(backend_tensor_device):
-    return backend_tensor_device
+def deal_lines(n_iter, rank: int, size: int, block: int = 32):
+    """This rank's share of deal_lines_all."""
+    return deal_lines_all(n_iter, size, block)[rank]
 
 
 def _comm_device():
@@ -73,27 +71,73 @@ def _comm_device():
     return torch.device("cpu")
 
 
-def all_gather_rows(local, counts=None):
-    """Concatenate per-rank row blocks (different lengths allowed) on every rank."""
+def _as_tensor(a, dev=None):
+    import torch
+
+    t = a if torch.is_tensor(a) else torch.as_tensor(np.ascontiguousarray(a))
+    if dev is not None and t.device != dev:
+        t = t.to(dev)
+    return t.contiguous()
+
+
+def all_gather_blocks(local, counts, out=None):
+    """Per-rank row blocks -> one (sum(counts), ...) tensor of the same dtype on every rank, rank
+    order.  `counts` (rows per rank) is known to every rank up front -- slabs, line deals and frame
+    deals are all deterministic -- so nothing but the payload is exchanged:
+      * equal counts: one all_gather_into_tensor straight into `out` (preallocated by the caller or
+        here), no staging and no copy;
+      * ragged counts: each block padded to the longest in a staging buffer (the blocks differ by
+        one row for slabs and frame deals), gathered with one all_gather_into_tensor, and the
+        valid rows copied into place."""
     import torch
 
     dist = _dist()
     rank, size = world()
-    t = local if torch.is_tensor(local) else torch.as_tensor(np.ascontiguousarray(local))
+    counts = [int(c) for c in counts]
+    dev = _comm_device() if size > 1 else None
+    t = _as_tensor(local, dev)
+    if t.shape[0] != counts[rank]:
+        raise ValueError(f"rank {rank} holds {t.shape[0]} rows, the plan says {counts[rank]}")
+    total = sum(counts)
+    tail = tuple(t.shape[1:])
+    if out is None:
+        out = torch.empty((total,) + tail, dtype=t.dtype, device=t.device)
+    elif tuple(out.shape) != (total,) + tail or out.dtype != t.dtype:
+        raise ValueError("all_gather_blocks: `out` has the wrong shape or dtype")
     if size == 1:
-        return t
-    dev = _comm_device()
-    t = t.to(dev).contiguous()
-    n_local = torch.tensor([t.shape[0]], dtype=torch.int64, device=dev)
-    ns = [torch.zeros_like(n_local) for _ in range(size)]
-    dist.all_gather(ns, n_local)
-    ns = [int(v.item()) for v in ns]
-    n_max = max(ns)
-    pad = torch.zeros((n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-    pad[: t.shape[0]] = t
-    bufs = [torch.empty_like(pad) for _ in range(size)]
-    dist.all_gather(bufs, pad)
-    return torch.cat([b[:n] for b, n in zip(bufs, ns)], dim=0)
+        out.copy_(t)
+        return out
+    if min(counts) == max(counts):
+        dist.all_gather_into_tensor(out, t)
+        return out
+    n_max = max(counts)
+    mine = torch.zeros((n_max,) + tail, dtype=t.dtype, device=t.device)
+    mine[: t.shape[0]] = t
+    stage = torch.empty((size * n_max,) + tail, dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(stage, mine)
+    lo = 0
+    for r, n in enumerate(counts):
+        out[lo:lo + n] = stage[r * n_max:r * n_max + n]
+        lo += n
+    return out
+
+
+def all_gather_rows(local, counts=None):
+    """Concatenate per-rank row blocks on every rank.  Without `counts` the block lengths are
+    exchanged first (one int64 per rank)."""
+    import torch
+
+    dist = _dist()
+    rank, size = world()
+    if size == 1:
+        return _as_tensor(local)
+    if counts is None:
+        dev = _comm_device()
+        n_local = torch.tensor([len(local)], dtype=torch.int64, device=dev)
+        ns = torch.empty(size, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(ns, n_local)
+        counts = ns.cpu().tolist()
+    return all_gather_blocks(local, counts)
 
 
 def all_reduce_(t, op="sum"):
@@ -113,32 +157,45 @@ def all_reduce_(t, op="sum"):
 
 
 # ------------------------------------------------------------------------------------------------
-def grid_sharded(compute, x0):
+def grid_sharded(compute, x0, out=None):
     """Field / ESP over a point list sharded by slabs.
     compute(points_slab) -> rows for that slab (torch tensor or ndarray, first dim = points).
-    Returns the full result, identical on every rank, in point order."""
+    Returns the full result, identical on every rank, in point order (gathered into `out` when given)."""
     rank, size = world()
     lo, hi = slab(len(x0), rank, size)
-    return all_gather_rows(compute(x0[lo:hi]))
+    counts = [slab(len(x0), r, size)[1] - slab(len(x0), r, size)[0] for r in range(size)]
+    return all_gather_blocks(compute(x0[lo:hi]), counts, out=out)
 
 
-def topo_sharded(compute, seeds, n_iter):
+def lattice_sharded(compute, xs, ys, zs, out=None):
+    """Field / ESP on the box mesh xs x ys x zs (z fastest, CPET/utils/calculator.py:218-233) sharded
+    by slabs of x-planes -- a contiguous slab of the flattened point list, so the gathered rows are in
+    the reference's point order.  compute(xs_slab, ys, zs) -> rows of that slab."""
+    rank, size = world()
+    lo, hi = slab(len(xs), rank, size)
+    plane = len(ys) * len(zs)
+    counts = [(slab(len(xs), r, size)[1] - slab(len(xs), r, size)[0]) * plane for r in range(size)]
+    return all_gather_blocks(compute(xs[lo:hi], ys, zs), counts, out=out)
+
+
+def topo_sharded(compute, seeds, n_iter, out=None):
     """Single-frame topology sharded by streamlines.
     compute(seeds_subset, n_iter_subset) -> (n,2) [dist|curv] rows in the order given.
-    Returns (L,2) in SEED order on every rank."""
+    Returns (L,2) in SEED order on every rank: the rows are gathered in rank order and scattered with
+    the permutation every rank derives from n_iter alone (deal_lines_all)."""
     import torch
 
     rank, size = world()
     seeds = np.asarray(seeds).reshape(-1, 3)
     n_iter = np.asarray(n_iter).reshape(-1)
-    ids = deal_lines(n_iter, rank, size)
+    deal = deal_lines_all(n_iter, size)
+    ids = deal[rank]
     local = compute(seeds[ids], n_iter[ids])
-    local = local if torch.is_tensor(local) else torch.as_tensor(np.ascontiguousarray(local))
-    idt = torch.as_tensor(ids.astype(np.int64)).to(local.device)
-    rows = torch.cat([idt.to(torch.float64).unsqueeze(1), local.to(torch.float64)], dim=1)
-    allrows = all_gather_rows(rows)
-    out = torch.empty((len(seeds), 2), dtype=local.dtype, device=allrows.device)
-    out[allrows[:, 0].to(torch.int64)] = allrows[:, 1:].to(local.dtype)
+    gathered = all_gather_blocks(local, [len(d) for d in deal])
+    perm = torch.as_tensor(np.concatenate(deal).astype(np.int64)).to(gathered.device)
+    if out is None:
+        out = torch.empty_like(gathered)
+    out[perm] = gathered
     return out
 
 
@@ -207,7 +264,8 @@ def frames_batch_sharded(compute_batch, n_frames):
     """Same, with one call per rank: compute_batch(ids) gets this rank's frame ids (rank, rank+size,
     ...) and returns one equal-shaped result per id (a list, or an array/tensor with leading
     dimension len(ids)) -- the shape of Math_ops.topo_hist_frames, which overlaps the copies and
-    kernels of neighbouring frames.  Results come back stacked in frame order on every rank."""
+    kernels of neighbouring frames.  Results come back stacked in frame order on every rank, in the
+    dtype they were computed in (int64 counts stay int64)."""
     import torch
 
     rank, size = world()
@@ -226,10 +284,12 @@ def frames_batch_sharded(compute_batch, n_frames):
     if not found:
         return torch.zeros(0)
     shape, dtype = found[0]
-    flat = (torch.stack(res).reshape(len(res), -1) if res
-            else torch.zeros((0, int(np.prod(shape))), dtype=dtype))
-    ids = torch.as_tensor(np.asarray(mine, dtype=np.float64)).reshape(-1, 1).to(flat.device)
-    rows = all_gather_rows(torch.cat([ids, flat.to(torch.float64)], dim=1))
-    out = torch.empty((n_frames,) + shape, dtype=flat.dtype, device=rows.device)
-    out[rows[:, 0].to(torch.int64)] = rows[:, 1:].to(flat.dtype).reshape((-1,) + shape)
+    local = torch.stack(res) if res else torch.zeros((0,) + shape, dtype=dtype)
+    counts = [len(frames_for_rank(n_frames, r, size)) for r in range(size)]
+    gathered = all_gather_blocks(local, counts)                   # rank-major: frames r, r+size, ...
+    out = torch.empty_like(gathered)
+    lo = 0
+    for r, n in enumerate(counts):
+        out[r::size] = gathered[lo:lo + n]
+        lo += n
     return out

@@ -233,6 +233,78 @@ def test_field_full_size_properties(M):
     assert relmax(phi[idx], f64.esp_grid(pts[idx], x, Q)) < FIELD_TOL
 
 
+def test_config3_esp_and_field_at_full_size(M):
+    """BASELINE configs[2] at its real size: 101^3 = 1,030,301 points x 100,000 charges through the
+    default host entry points (mesh recognition -> lattice kernel, charge-range splits + FP64
+    finalize as the launcher decides), against the float64 oracle on 4,096 sampled points, in the
+    reference's return layouts ((N,6) f32 [x|E], (N,4) f16 [x|phi], UC:446-447, 473-475)."""
+    x, Q = synth.charges(100_000, seed=3, box=5.0)
+    pts = synth.grid(101, 5.0)
+    assert len(pts) == 1_030_301 and len(Q) == 100_000
+    reset_tuning(M)
+    M.set_charges(x, Q)
+    e = M.field_grid(pts, soften=True, concat=True)
+    assert M.last_path() == "lattice"
+    assert e.shape == (len(pts), 6) and e.dtype == np.float32
+    np.testing.assert_array_equal(e[:, :3], pts)
+    idx = np.random.default_rng(7).choice(len(pts), 4096, replace=False)
+    assert relmax(e[idx, 3:], f64.field_grid(pts[idx], x, Q, True)) < FIELD_TOL
+    phi_ref = f64.esp_grid(pts[idx], x, Q)
+    phi = M.esp_grid(pts)
+    assert M.last_path() == "lattice"
+    assert relmax(phi[idx], phi_ref) < FIELD_TOL
+    half = M.esp_grid(pts, concat_half=True)
+    assert half.shape == (len(pts), 4) and half.dtype == np.float16
+    np.testing.assert_array_equal(half[:, :3], pts.astype(np.float16))
+    with np.errstate(over="ignore"):
+        np.testing.assert_array_equal(half[idx, 3], phi[idx].astype(np.float16))   # same f32 -> f16 rounding as .astype(np.half)
+    # the same points in another order take the general kernel: same values within the field budget
+    perm = np.random.default_rng(8).permutation(len(pts))[:200_000]
+    eg = M.field_grid(pts[perm], soften=True)
+    assert M.last_path() == "general"
+    assert relmax(eg, e[perm, 3:]) < 2e-6
+
+
+def test_sweep_corner_1e8_points(M):
+    """BASELINE configs[4] corner N = 464^3 = 99,897,344 points (x 1,000 charges), device-resident
+    through the _dev C ABI: 2.4 GB of (N,6) rows written by the kernel, point indices beyond 2^24,
+    6 N floats beyond 2^29.  Oracle parity on 4,096 sampled rows; the lattice entry point and the
+    point-list entry point must give the same bits on the sampled rows."""
+    import torch
+
+    from pycpet_b200.device import Engine
+
+    x, Q = synth.charges(1000, seed=9, box=1.5)
+    n = 464
+    c = np.linspace(-1.5, 1.5, n)
+    c32 = c.astype(np.float32)
+    eng = Engine(0)
+    eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
+    ax = torch.from_numpy(c32).cuda()
+    out = eng.field_lattice(ax, ax, ax, soften=True, concat=True)
+    assert out.shape == (n ** 3, 6)
+    rng = np.random.default_rng(11)
+    idx = np.unique(np.concatenate([rng.choice(n ** 3, 4090, replace=False),
+                                    [0, n ** 3 - 1, 2 ** 24 + 1, 2 ** 26 + 3, n ** 3 - n, n ** 3 // 2]]))
+    rows = out[torch.from_numpy(idx).cuda()].cpu().numpy()
+    ix, iy, iz = np.unravel_index(idx, (n, n, n))
+    pts = np.column_stack([c32[ix], c32[iy], c32[iz]])
+    np.testing.assert_array_equal(rows[:, :3], pts)                   # z fastest, meshgrid(indexing="ij")
+    assert relmax(rows[:, 3:], f64.field_grid(pts, x, Q, True)) < FIELD_TOL
+    phi = eng.esp_lattice(ax, ax, ax)
+    assert relmax(phi[torch.from_numpy(idx).cuda()].cpu().numpy(), f64.esp_grid(pts, x, Q)) < FIELD_TOL
+    del phi
+    # the general point-list kernel on the last 2^25 points of the same mesh (indices near the top of the range)
+    tail = 2 ** 25
+    g = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1).reshape(-1, 3)[-tail:].contiguous()
+    eg = eng.field_grid(g, soften=True)
+    sel = idx[idx >= n ** 3 - tail]
+    got = eg[torch.from_numpy(sel - (n ** 3 - tail)).cuda()].cpu().numpy()
+    want = rows[np.isin(idx, sel), 3:]
+    assert relmax(got, want) < 2e-6
+    eng.close()
+
+
 @pytest.mark.parametrize("shape", [(11, 11, 11), (5, 7, 23), (3, 2, 101), (6, 5, 4), (2, 3, 1)])
 def test_field_lattice_matches_general_kernel(M, frame2a, shape):
     """The lattice kernel (dx, dy shared along z) against the general kernel on the expanded mesh:
@@ -659,6 +731,41 @@ def test_topo_full_size_3A_properties(M, frame2a):
     idx = rng.choice(len(seeds), 1500, replace=False)
     want, wsteps = f64.topo_batch(seeds[idx], n_iter[idx], x, Q, 0.1, dims)
     check_lines(got[idx], steps[idx], want, wsteps, 0.1, curv_tol_dir(0.1))
+
+
+def test_config4_frame_of_one_million_seeds(M, frame2a):
+    """One frame of BASELINE configs[3] at its real size: 100^3 = 1,000,000 seeds x 7,890 charges
+    (queue sort with 1e6 keys, 4 lines per warp, 1e6 queue refills).  Oracle parity on 2,048 sampled
+    lines, the work-counter identities the bench's `value` relies on, the same bits from the
+    round-1 direct-form kernel's bookkeeping (steps), and the frame's histogram against NumPy."""
+    x, Q = frame2a
+    seeds, n_iter, dims, max_steps = synth.seeds(100, 0.5, 0.1)
+    assert len(seeds) == 1_000_000 and max_steps == 17
+    reset_tuning(M)
+    got, steps = M.topo_batch(seeds, n_iter, x, Q, 0.1, dims, want_steps=True)
+    c = M.last_counters()
+    assert np.all(steps >= 1) and np.all(steps <= n_iter)
+    assert np.all(np.isfinite(got)) and np.all(got[:, 1] >= 0)
+    assert np.all(got[:, 0] <= steps * 0.1 * (1 + 1e-5) + 1e-6)
+    evals = int(steps.astype(np.int64).sum() + 2 * len(steps))
+    assert c["field_evals"] == evals and c["pair_evals"] == evals * len(Q)
+    idx = np.random.default_rng(3).choice(len(seeds), 2048, replace=False)
+    want, wsteps = f64.topo_batch(seeds[idx], n_iter[idx], x, Q, 0.1, dims)
+    check_lines(got[idx], steps[idx], want, wsteps, 0.1, curv_tol_dir(0.1))
+    # a line's result does not depend on the batch it was computed in
+    sub = M.topo_batch(seeds[idx], n_iter[idx], x, Q, 0.1, dims)
+    np.testing.assert_array_equal(sub, got[idx])
+    # the direct-form kernel walks the same lines (a step-count flip needs a point within rounding of a box face)
+    M.set_tuning(k2_form=1)
+    got1, steps1 = M.topo_batch(seeds, n_iter, x, Q, 0.1, dims, want_steps=True)
+    reset_tuning(M)
+    assert (steps1 != steps).sum() <= 20
+    same = steps1 == steps
+    assert np.max(np.abs(got1[same, 0] - got[same, 0])) <= 2e-6
+    de, ce = np.linspace(0.0, 1.8, 51), np.linspace(0.0, float(got[:, 1].max()), 51)
+    np.testing.assert_array_equal(M.hist2d(got, de, ce),
+                                  np.histogram2d(got[:, 0].astype(np.float64), got[:, 1].astype(np.float64),
+                                                 bins=[de, ce])[0].astype(np.int64))
 
 
 # ------------------------------------------------------------------------------------ K3 --------

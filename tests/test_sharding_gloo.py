@@ -49,6 +49,14 @@ def _worker(rank, size, port, tmp):
     seeds, n_iter, dims, _ = synth.seeds(4, 0.5, 0.1)
 
     full_field = sharding.grid_sharded(lambda p: f64.field_grid(p, x, Q, True), pts).numpy()
+    # the same mesh by slabs of x-planes (5 planes over 2 ranks: ragged 3 + 2), gathered into a caller buffer
+    ax = np.linspace(-0.5, 0.5, 5)
+    lat_out = torch.empty((125, 3), dtype=torch.float64)
+    def lattice_rows(xs, ys, zs):
+        g = np.stack(np.meshgrid(xs, ys, zs, indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+        return f64.field_grid(g, x, Q, True)
+    got = sharding.lattice_sharded(lattice_rows, ax, ax, ax, out=lat_out)
+    assert got is lat_out
     full_topo = sharding.topo_sharded(lambda s, n: f64.topo_batch(s, n, x, Q, 0.1, dims)[0], seeds, n_iter).numpy()
     # histogram of the lines held by this rank, reduced
     ids = sharding.deal_lines(n_iter, rank, size)
@@ -70,7 +78,7 @@ def _worker(rank, size, port, tmp):
     n_all = len(ref_topo)
     stats = sharding.order_stats_sharded(lambda pre, bits: np_radix_hist(mine32, pre, bits),
                                          [0, n_all // 4, n_all // 2, (3 * n_all) // 4, n_all - 1])
-    np.savez(os.path.join(tmp, f"r{rank}.npz"), field=full_field, topo=full_topo, counts=counts,
+    np.savez(os.path.join(tmp, f"r{rank}.npz"), lattice=lat_out.numpy(), field=full_field, topo=full_topo, counts=counts,
              frames=frames, batch=batch, lone=lone, ranges=np.array([lo_d, hi_d, lo_c, hi_c]), stats=stats)
     dist.destroy_process_group()
 
@@ -89,6 +97,7 @@ def test_world_size_2_gloo(tmp_path):
     for r in range(2):
         z = np.load(tmp_path / f"r{r}.npz")
         np.testing.assert_array_equal(z["field"], field)
+        np.testing.assert_array_equal(z["lattice"], field)
         np.testing.assert_array_equal(z["topo"], topo)
         rg = z["ranges"]
         assert rg[0] == topo[:, 0].min() and rg[1] == topo[:, 0].max()

@@ -15,7 +15,7 @@ using namespace cpet;
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
 
-struct __align__(16) V16 { u64 a, b; };
+// V16 comes from common.cuh
 // one block = 32 pairs; per-lane vectors: v0[32] (16 B), v1[32] (16 B), v2[32] (8 B)
 struct __align__(16) UBlock { V16 v0[32]; V16 v1[32]; u64 v2[32]; };
 
