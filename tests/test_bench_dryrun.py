@@ -39,6 +39,10 @@ class FakeEvent:
         return other.t - self.t
 
 
+def _frame_code(tag):
+    return int(abs(tag) * 1e6) % 100003
+
+
 class FakeEngine:
     """Stand-in for pycpet_b200.device.Engine: same method names, no device."""
     instances = []
@@ -68,13 +72,17 @@ class FakeEngine:
         self.calls["topo_batch"] += 1
         self.units = int(seeds.shape[0])
         self.times.append(K_MS)
+        if out is None:
+            out = torch.zeros((self.units, 2), dtype=torch.float32)
         out.zero_()
         return out
 
     def hist2d(self, values, d_edges, c_edges, out=None):
         self.calls["hist2d"] += 1
         self.times.append(0.01)
-        out.fill_(self.calls["hist2d"])
+        if out is None:
+            out = torch.zeros((1, len(d_edges) - 1, len(c_edges) - 1), dtype=torch.int64)
+        out.fill_(_frame_code(self.frame_tag))          # a frame's histogram depends on the frame only
         return out
 
     def field_grid(self, x0, soften=True, concat=False, out=None):
@@ -87,12 +95,26 @@ class FakeEngine:
         self.calls["grid"] += 1
         self.units = int(xs.numel() * ys.numel() * zs.numel())
         self.times.append(K_MS)
+        if out is None:
+            out = torch.ones((self.units, 6), dtype=torch.float32)
+        else:
+            out.fill_(1.0)
         return out
 
     def esp_grid(self, x0, concat_half=False, out=None):
         self.calls["grid"] += 1
         self.units = int(x0.shape[0])
         self.times.append(K_MS)
+        return out
+
+    def esp_lattice(self, xs, ys, zs, concat_half=False, out=None):
+        self.calls["grid"] += 1
+        self.units = int(xs.numel() * ys.numel() * zs.numel())
+        self.times.append(K_MS)
+        if out is None:
+            out = torch.ones((self.units, 4), dtype=torch.float16)
+        else:
+            out.fill_(1.0)
         return out
 
     def last_counters(self):
@@ -121,6 +143,8 @@ class FakeMath:
         assert n_iter.shape == (len(frames), len(seeds))
         assert rows_out.shape == (len(frames), len(seeds), 2) and counts_out.shape[0] == len(frames)
         FakeMath.frames_calls.append([float(np.asarray(fx).reshape(-1)[0]) for fx, _ in frames])
+        for k, (fx, _) in enumerate(frames):
+            counts_out[k] = _frame_code(float(np.asarray(fx).reshape(-1)[0]))
         return rows_out, counts_out
 
     def field_grid(self, x_0, x=None, Q=None, soften=True, concat=False, out=None):
@@ -160,8 +184,8 @@ def _install(monkey_set):
     return bench
 
 
-def _args(workload, steps=5, warmup=3):
-    return argparse.Namespace(gpus=1, steps=steps, warmup=warmup, workload=workload, impl="b200", cpu_seconds=None)
+def _args(workload, steps=5, warmup=3, **kw):
+    return argparse.Namespace(gpus=1, steps=steps, warmup=warmup, workload=workload, impl="b200", cpu_seconds=None, **kw)
 
 
 CONTRACT_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
@@ -211,7 +235,7 @@ def test_topo_accounting_single_rank(bench_mod):
     assert line["gpu_launches"] == steps * (1 + 4 + 1)
     # roofline: 20 flop x mean pair-evals per timed step / the integrator's own duration
     r = line["roofline"]
-    assert r["kernel"] == "k2w_topo_kernel" and r["kernel_ms"] == pytest.approx(K_MS)
+    assert r["kernel"] == "k2x_topo_kernel" and r["kernel_ms"] == pytest.approx(K_MS)
     assert r["achieved"] == pytest.approx(want_pairs / steps * 20.0 / (K_MS * 1e-3) / 1e12)
     assert r["peak"] == 73.4 and r["frac"] == pytest.approx(r["achieved"] / 73.4)
     # end-to-end arm: one warm-up call and ONE timed call of `steps` frames, in the rotation of the device arm
@@ -220,6 +244,37 @@ def test_topo_accounting_single_rank(bench_mod):
     e = line["e2e"]
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 125 * 8 + 50 * 50 * 8
     assert e["value"] > 0 and e["unit"] == line["unit"]
+    # the end-to-end call's histograms were compared with the device arm's
+    assert line["parity_checked"] is True and "end-to-end" in line["parity"]
+    assert line["step_ms_by_rank"]["median"] == [pytest.approx(STEP_MS / 2.0)]
+    assert "sustained" not in line and "others" not in line
+
+
+def test_sustained_and_other_workloads_ride_on_the_default_line(bench_mod):
+    """N = 1: a sustained run of the same step loop after the timed region and one short record per
+    other BASELINE configuration."""
+    bench = bench_mod
+    steps = 4
+    line = bench.run_gpu(_args("topo3a", steps, 3, sustained=0.25, others=["md1m", "volume", "esp101", "topo3a"]),
+                         rank=0, world=1, local_rank=0)
+    json.dumps(line)
+    s = line["sustained"]
+    # fake clock: 1 ms per step bracket, batches of 100 steps until 0.25 s of busy time
+    assert s["steps"] == 300 and s["seconds"] == pytest.approx(0.3) and s["ms_per_step"] == pytest.approx(1.0)
+    eng = FakeEngine.instances[0]
+    by_tag = {}
+    for t in eng.frames_seen[:bench.FRAME_POOL]:
+        eng.frame_tag = t
+        by_tag[t] = eng._pairs(125)
+    first = bench.FRAME_POOL + 3 + steps                      # steps issued before the sustained loop
+    want = sum(by_tag[t] for t in eng.frames_seen[first:first + 300])
+    assert s["value"] == pytest.approx(want / 0.3, rel=1e-12)
+    assert sorted(line["others"]) == ["esp101", "md1m", "volume"]          # the line's own workload is not repeated
+    for name, o in line["others"].items():
+        assert o["value"] > 0 and o["e2e"]["value"] > 0 and o["roofline"]["kernel_ms"] == pytest.approx(K_MS)
+        assert "cpu_baseline" not in o and "sustained" not in o
+    assert line["others"]["esp101"]["roofline"]["mufu_frac"] > 0
+    assert line["others"]["volume"]["roofline"]["kernel"] == "k1_grid_kernel"      # 5^3 points: below the mesh threshold
 
 
 def test_long_runs_keep_the_integrator_times(bench_mod):
@@ -230,7 +285,7 @@ def test_long_runs_keep_the_integrator_times(bench_mod):
 
 
 @pytest.mark.parametrize("workload,kernel", [("volume", "k1_grid_kernel"), ("esp101", "k1_grid_kernel"),
-                                             ("volume2a", "k1_grid_kernel")])
+                                             ("volume2a", "k1_grid_kernel")])   # 5^3 points: below the mesh threshold
 def test_grid_accounting_single_rank(bench_mod, workload, kernel):
     bench = bench_mod
     steps = 4
@@ -289,6 +344,54 @@ def _worker(rank, size, port, tmp):
     dist.destroy_process_group()
 
 
+def _split_worker(rank, size, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+
+    def monkey_set(obj, name, value, item=False):
+        if item:
+            obj[name] = value
+        else:
+            setattr(obj, name, value)
+
+    bench = _install(monkey_set)
+    out = {}
+    for workload, split in (("md1m", "seeds"), ("volume464", "slab"), ("esp464", "slab")):
+        FakeEngine.instances.clear()
+        line = bench.run_split(_args(workload, 4, 3, split=split), rank=rank, world=size, local_rank=0)
+        eng = FakeEngine.instances[0]
+        out[workload] = {"line": line, "units": eng.units}
+    with open(os.path.join(tmp, f"split{rank}.json"), "w") as fh:
+        json.dump(out, fh)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_strong_scaling_splits_over_gloo(tmp_path):
+    """--split seeds / slab with world_size 2: the shards partition the frame, `value` credits the
+    whole frame once per step, the line says "strong"."""
+    mp.spawn(_split_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    r0 = json.load(open(tmp_path / "split0.json"))
+    r1 = json.load(open(tmp_path / "split1.json"))
+    timed_s = 4 * 3 * (STEP_MS / 2.0) * 1e-3     # per step: the bracket's closing record + the two gather-timing records inside it
+    for workload, n_units in (("md1m", 125), ("volume464", 125), ("esp464", 125)):
+        line = r0[workload]["line"]
+        assert r1[workload]["line"] is None
+        # rank 1 holds about half of the frame (rank 0 ends on the unsharded parity run); the work credited
+        # per step is the whole frame's: shards of 125 units sum to a multiple of 125 x the per-unit work
+        assert 50 <= r1[workload]["units"] <= 75 and r0[workload]["units"] == n_units
+        assert line["config"]["pair_evals_per_step"] % n_units == 0
+        assert line["parity_checked"] is True
+        for k in CONTRACT_KEYS:
+            assert k in line, k
+        assert line["scaling"] == "strong" and line["n_gpus"] == 2
+        assert line["config"]["units_per_step"] == n_units
+        assert line["value"] == pytest.approx(line["config"]["pair_evals_per_step"] * 4 / timed_s)
+        assert len(line["limiter"]["rank_kernel_ms"]) == 2
+        assert line["e2e"]["d2h_bytes_per_step"] > 0 and line["e2e"]["value"] > 0
+
+
 @pytest.mark.timeout(300)
 def test_two_ranks_over_gloo(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
@@ -298,6 +401,9 @@ def test_two_ranks_over_gloo(tmp_path):
         assert k in line, k
     assert "cpu_baseline" not in line             # rank 0 times the CPU reference at N = 1 only
     assert line["n_gpus"] == 2
+    # every gathered histogram of the timed steps (7 steps x 2 ranks) was compared with rank 0's own
+    assert line["parity_checked"] is True and "14 gathered" in line["parity"]
+    assert len(line["step_ms_by_rank"]["median"]) == 2
     timed_s = (7 + 1) * (STEP_MS / 2.0) * 1e-3    # both ranks report the same fake time; the max is that time
     assert line["value"] == pytest.approx(d["pairs_all"] / timed_s)          # work summed over ranks
     assert line["units_per_s"] == pytest.approx(2 * 125 * 7 / timed_s)
