@@ -209,6 +209,11 @@ int cpet_radix_hist_dev(cpet_ctx *ctx, int64_t n, const float *d_values, int str
  * out[i][j] = 1/2 sum_{b: h_i[b]+h_j[b] != 0} (h_i[b]-h_j[b])^2 / (h_i[b]+h_j[b]); diagonal 0.
  * H: (n_hists, n_bins) float64 host; out: (n_hists, n_hists) float64 host. */
 int cpet_chi2_matrix(cpet_ctx *ctx, int n_hists, int64_t n_bins, const double *H, double *out);
+/* Rows [row0, row0 + n_rows) of that matrix from device-resident histograms (the share of one GPU when
+ * construct_distance_matrix, UC:1003-1015, is split over ranks; both triangles carry the same bits).
+ * d_H: (n_hists, n_bins) float64 device; d_out: (n_rows, n_hists) float64 device; asynchronous. */
+int cpet_chi2_rows_dev(cpet_ctx *ctx, int n_hists, int64_t n_bins, const double *d_H, int row0,
+                       int n_rows, double *d_out);
 
 /* ---------------------------------------------------------------- text outputs ------------- */
 /* Byte-compatible replacement for the np.savetxt calls that write the path's results: `.top`

@@ -79,6 +79,7 @@ SIGNATURES = {
     "cpet_order_stats_dev": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "cpet_radix_hist_dev": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "cpet_chi2_matrix": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "cpet_chi2_rows_dev": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_void_p]),
     "cpet_write_rows": (c_int, [ctypes.c_char_p, ctypes.c_char_p, c_void_p, c_int, c_int64, c_int,
                                 ctypes.c_char_p, c_int]),
     "cpet_count_rows": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_int64), c_int]),

@@ -808,6 +808,15 @@ int cpet_chi2_matrix(cpet_ctx* c, int n_hists, int64_t n_bins, const double* H, 
     return CPET_OK;
 }
 
+int cpet_chi2_rows_dev(cpet_ctx* c, int n_hists, int64_t n_bins, const double* d_H, int row0, int n_rows,
+                       double* d_out) {
+    CTX_GUARD(c);
+    CPET_REQUIRE(n_hists >= 0 && n_bins >= 0 && n_rows >= 0, CPET_ERR_INVALID, "negative sizes");
+    if (n_hists == 0 || n_rows == 0) return CPET_OK;
+    CPET_REQUIRE(d_H && d_out, CPET_ERR_INVALID, "NULL arrays");
+    return launch_chi2_rows(c, n_hists, n_bins, d_H, row0, n_rows, d_out);
+}
+
 int cpet_fp32_peak_probe(cpet_ctx* c, int packed, int iters, double* tflops) {
     CTX_GUARD(c);
     CPET_REQUIRE(tflops != nullptr, CPET_ERR_INVALID, "tflops is NULL");

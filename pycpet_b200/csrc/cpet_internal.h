@@ -111,6 +111,8 @@ int launch_hist2d(cpet_ctx* c, int n_frames, int64_t n_per_frame, const void* d_
                   bool values_f64, int nd, const double* d_edges_dev, int nc,
                   const double* c_edges_dev, unsigned long long* d_counts);
 int launch_chi2(cpet_ctx* c, int n_hists, int64_t n_bins, const double* d_H, double* d_out);
+int launch_chi2_rows(cpet_ctx* c, int n_hists, int64_t n_bins, const double* d_H, int row0, int n_rows,
+                     double* d_out);
 int launch_radix_hist(cpet_ctx* c, long long n, const float* d_values, int stride, int offset,
                       int n_targets, const unsigned* d_prefixes, int prefix_bits,
                       unsigned long long* d_hist);

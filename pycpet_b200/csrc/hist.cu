@@ -139,13 +139,27 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const float* __restrict
     if (threadIdx.x < n_targets) pre[threadIdx.x] = prefixes[threadIdx.x];
     __syncthreads();
     const int shift = 24 - prefix_bits;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+    const int lane = threadIdx.x & 31;
+    // whole warps stay in the loop (match.any needs a full mask); the values of a frame cluster in a few
+    // exponent bins, so the lanes of a warp are aggregated per (target, bin) before the shared atomic
+    const long long n_round = ((n + 31) / 32) * 32;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round;
          i += (long long)gridDim.x * blockDim.x) {
-        const unsigned key = monotone_key(values[i * stride + offset]);
-        const unsigned head = prefix_bits ? (key >> (32 - prefix_bits)) : 0u;
+        unsigned key = 0u, head = 0u;
+        const bool live = i < n;
+        if (live) {
+            key = monotone_key(values[i * stride + offset]);
+            head = prefix_bits ? (key >> (32 - prefix_bits)) : 0u;
+        }
         const unsigned bin = (key >> shift) & 255u;
-        for (int t = 0; t < n_targets; ++t)
-            if (prefix_bits == 0 || head == pre[t]) atomicAdd(&cnt[t][bin], 1u);
+        // targets may share a prefix (neighbouring ranks): every matching target gets the count
+        const unsigned long long tag = live ? (((unsigned long long)head << 8) | bin) : (1ull << 40);   // NaN keys are all ones
+        const unsigned peers = __match_any_sync(0xffffffffu, tag);
+        if (live && lane == __ffs(peers) - 1) {
+            const unsigned add = (unsigned)__popc(peers);
+            for (int t = 0; t < n_targets; ++t)
+                if (prefix_bits == 0 || head == pre[t]) atomicAdd(&cnt[t][bin], add);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n_targets * 256; i += blockDim.x)
@@ -200,6 +214,47 @@ __global__ void __launch_bounds__(256) chi2_kernel(const double* __restrict__ H,
         out[(size_t)i * n + j] = d;
         out[(size_t)j * n + i] = d;
     }
+}
+
+// Rows [row0, row0 + n_rows) of the same matrix (every column, both triangles): the unit a rank computes when
+// the matrix of a trajectory is split over GPUs.  blockIdx.x = column, so the CTAs in flight share row i.
+__global__ void __launch_bounds__(256) chi2_rows_kernel(const double* __restrict__ H, int n, long long nbins,
+                                                        int row0, double* __restrict__ out) {
+    const int i = row0 + blockIdx.y, j = blockIdx.x;
+    double* o = out + (size_t)blockIdx.y * n + j;
+    if (j == i) { if (threadIdx.x == 0) *o = 0.0; return; }
+    // the same operand order as the (i < j) entry of chi2_kernel, so both triangles carry the same bits
+    const double* a = H + (size_t)(i < j ? i : j) * nbins;
+    const double* b = H + (size_t)(i < j ? j : i) * nbins;
+    double s = 0.0;
+    for (long long k = threadIdx.x; k < nbins; k += blockDim.x) {
+        const double x = a[k], y = b[k];
+        const double sum = x + y;
+        const double diff = x - y;
+        if (sum != 0.0) s += diff * diff / sum;
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w >= 1; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *o = 0.5 * red[0];
+}
+
+int launch_chi2_rows(cpet_ctx* c, int n_hists, int64_t n_bins, const double* d_H, int row0, int n_rows,
+                     double* d_out) {
+    c->last_counters[0] = 0;
+    if (n_hists == 0 || n_rows == 0) return CPET_OK;
+    CPET_REQUIRE(n_hists <= 65535 && n_rows <= 65535, CPET_ERR_INVALID, "chi2 matrix limited to 65535 histograms");
+    CPET_REQUIRE(row0 >= 0 && row0 + n_rows <= n_hists, CPET_ERR_INVALID, "row block outside the matrix");
+    KernelTimer timer(c);
+    dim3 grid((unsigned)n_hists, (unsigned)n_rows, 1);
+    chi2_rows_kernel<<<grid, 256, 0, c->stream>>>(d_H, n_hists, (long long)n_bins, row0, d_out);
+    CPET_CUDA_TRY(cudaGetLastError());
+    c->last_counters[0] = 1;
+    return CPET_OK;
 }
 
 int launch_chi2(cpet_ctx* c, int n_hists, int64_t n_bins, const double* d_H, double* d_out) {

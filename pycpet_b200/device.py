@@ -206,3 +206,19 @@ class Engine:
                                        _lib.ptr(ce), _p(out)))
         self._keep3 = (v, de, ce)
         return out[0] if single else out
+
+    def chi2_rows(self, hists, row0=0, n_rows=None, out=None):
+        """Rows [row0, row0 + n_rows) of the pairwise chi^2 distance matrix (UC:975-978, 1003-1015) of
+        device-resident float64 histograms (F, n_bins) -> (n_rows, F) float64 CUDA tensor."""
+        torch = self.torch
+        h = hists
+        if h.dtype != torch.float64 or not h.is_contiguous() or h.device != self.device:
+            h = h.to(device=self.device, dtype=torch.float64).contiguous()
+        h = h.reshape(h.shape[0], -1)
+        f = int(h.shape[0])
+        n_rows = f - row0 if n_rows is None else int(n_rows)
+        if out is None:
+            out = torch.empty((n_rows, f), dtype=torch.float64, device=self.device)
+        check(self.lib.cpet_chi2_rows_dev(self.ctx, f, int(h.shape[1]), _p(h), int(row0), n_rows, _p(out)))
+        self._keep5 = h
+        return out

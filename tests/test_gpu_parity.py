@@ -926,6 +926,55 @@ def test_make_histograms_and_chi2_pinned_to_the_reference(M, golden, tmp_path):
     np.testing.assert_array_equal((cnt / cnt.sum()).flatten(), g["grid_fixed"])
 
 
+def test_trajectory_pipeline_matches_make_histograms(M, frame2a, tmp_path):
+    """pycpet_b200.trajectory (rows stay in HBM: K2 -> radix-select bin plan -> batched K3 -> chi^2 rows)
+    against the file-based route the reference takes for the same frames: .top text per frame ->
+    calculator.make_histograms (host scipy IQR plan) -> construct_distance_matrix."""
+    import torch
+
+    from pycpet_b200 import calculator as calc, trajectory
+    from pycpet_b200.device import Engine
+    from pycpet_b200.io import save_topology
+
+    x, Q = frame2a
+    seeds, n_iter, dims, _ = synth.seeds(16, 0.5, 0.1)
+
+    def frame(f):
+        rng = np.random.default_rng(300 + f)
+        xf = (x + rng.normal(0, 0.3, x.shape)).astype(np.float32)
+        xf[np.all(np.abs(xf) < 0.55, axis=1)] *= 3.0
+        return torch.from_numpy(xf).cuda(), torch.from_numpy(Q).cuda()
+
+    eng = Engine(0)
+    tr = trajectory.topology_trajectory(eng, 7, frame, seeds, n_iter, 0.1, dims)
+    rows = tr["rows"].cpu().numpy()
+    assert rows.shape == (7, 4096, 2) and tr["frames"] == list(range(7))
+    files = []
+    for f in range(7):
+        p = str(tmp_path / f"frame{f}.top")
+        save_topology(p, rows[f])
+        files.append(p)
+    want = calc.make_histograms(files)
+    assert tr["plan"] == calc.bin_plan([r.astype(np.float64) for r in rows])
+    np.testing.assert_array_equal(tr["hists"].cpu().numpy(), want)
+    np.testing.assert_allclose(tr["distance"].cpu().numpy(), calc.construct_distance_matrix(want), rtol=1e-13, atol=0)
+    np.testing.assert_allclose(tr["distance"].cpu().numpy(), ohist.chi2_matrix(want), rtol=1e-12, atol=0)
+    # a row block of the matrix carries the bits of the full matrix, both triangles
+    full = eng.chi2_rows(tr["hists"]).cpu().numpy()
+    np.testing.assert_array_equal(full, full.T)
+    np.testing.assert_array_equal(eng.chi2_rows(tr["hists"], 2, 3).cpu().numpy(), full[2:5])
+    np.testing.assert_array_equal(full, M.chi2_matrix(want))
+    # work accounting: sum over frames and lines of (K + 2) x M
+    total = 0
+    for f in range(7):
+        xf, Qf = frame(f)
+        eng.set_charges(xf, Qf)
+        _, st = eng.topo_batch(torch.from_numpy(seeds).cuda(), n_iter, 0.1, dims, want_steps=True)
+        total += int(st.sum().item() + 2 * len(seeds)) * len(Q)
+    assert tr["pair_evals"] == total
+    eng.close()
+
+
 def test_topo_hist_fused_call(M, frame2a):
     """cpet_topo_hist = cpet_topo_batch + cpet_hist2d with the rows kept on the device."""
     x, Q = frame2a

@@ -34,6 +34,53 @@ def np_radix_hist(values, prefixes, prefix_bits):
     return out
 
 
+class OracleEngine:
+    """Host stand-in with the Engine methods pycpet_b200.trajectory uses, computing with the oracle
+    (float64 streamlines rounded to float32 rows, NumPy histograms): what is under test is the
+    trajectory pipeline's partitioning, its all-reduced radix select and its gathers."""
+
+    def __init__(self):
+        from oracle import f64, hist as ohist
+        self.f64, self.ohist = f64, ohist
+        self.device = torch.device("cpu")
+        self.n_charges = 0
+
+    def set_charges(self, x, Q):
+        self.x, self.Q = np.asarray(x, np.float32), np.asarray(Q, np.float32)
+        self.n_charges = len(self.Q)
+
+    def topo_batch(self, seeds, n_iter, step_size, dimensions, second_diff=False, out=None, steps=None):
+        rows, st = self.f64.topo_batch(seeds.numpy(), n_iter.numpy().astype(np.int64), self.x, self.Q, step_size,
+                                       dimensions)
+        out.copy_(torch.from_numpy(rows.astype(np.float32)))
+        if steps is not None:
+            steps.copy_(torch.from_numpy(st.astype(np.int32)))
+        return out
+
+    def radix_hist(self, values, column, prefixes, prefix_bits):
+        return np_radix_hist(values.numpy()[:, column], prefixes, prefix_bits)
+
+    def hist2d(self, values, d_edges, c_edges):
+        v = values.numpy().astype(np.float64)
+        return torch.from_numpy(np.stack([
+            np.histogram2d(f[:, 0], f[:, 1], bins=[d_edges, c_edges])[0].astype(np.int64) for f in v]))
+
+    def chi2_rows(self, hists, row0=0, n_rows=None):
+        return torch.from_numpy(self.ohist.chi2_matrix(hists.numpy())[row0:row0 + n_rows].copy())
+
+
+def _trajectory_inputs():
+    x, Q = synth.charges(300, seed=2, box=0.5)
+    seeds, n_iter, dims, _ = synth.seeds(6, 0.5, 0.1)
+
+    def frame(f):
+        rng = np.random.default_rng(50 + f)
+        xf = (x + rng.normal(0, 0.3, x.shape)).astype(np.float32)
+        xf[np.all(np.abs(xf) < 0.55, axis=1)] *= 3.0
+        return xf, Q
+    return frame, seeds, n_iter, dims
+
+
 def _worker(rank, size, port, tmp):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -78,6 +125,14 @@ def _worker(rank, size, port, tmp):
     n_all = len(ref_topo)
     stats = sharding.order_stats_sharded(lambda pre, bits: np_radix_hist(mine32, pre, bits),
                                          [0, n_all // 4, n_all // 2, (3 * n_all) // 4, n_all - 1])
+    # the device-resident trajectory pipeline (5 frames over 2 ranks: 3 + 2) with the oracle as the engine
+    from pycpet_b200 import trajectory
+    frame, tseeds, tn_iter, tdims = _trajectory_inputs()
+    tr = trajectory.topology_trajectory(OracleEngine(), 5, frame, tseeds, tn_iter, 0.1, tdims)
+    assert tr["frames"] == list(range(rank, 5, size)) and tr["rows"].shape == (len(tr["frames"]), 216, 2)
+    np.savez(os.path.join(tmp, f"traj{rank}.npz"), plan=np.array([*tr["plan"][0], *tr["plan"][1], tr["plan"][2], tr["plan"][3]]),
+             counts=tr["counts"].numpy(), hists=tr["hists"].numpy(), distance=tr["distance"].numpy(),
+             pairs=np.array([tr["pair_evals"]]))
     np.savez(os.path.join(tmp, f"r{rank}.npz"), lattice=lat_out.numpy(), field=full_field, topo=full_topo, counts=counts,
              frames=frames, batch=batch, lone=lone, ranges=np.array([lo_d, hi_d, lo_c, hi_c]), stats=stats)
     dist.destroy_process_group()
@@ -111,3 +166,26 @@ def test_world_size_2_gloo(tmp_path):
         srt = np.sort(topo[:, 1].astype(np.float32))
         n_all = len(srt)
         np.testing.assert_array_equal(z["stats"], srt[[0, n_all // 4, n_all // 2, (3 * n_all) // 4, n_all - 1]])
+    # trajectory pipeline: what calculator.bin_plan / make_histograms / construct_distance_matrix's rule give
+    # on the host for the same five frames, on every rank
+    from pycpet_b200 import calculator as calc
+    frame, tseeds, tn_iter, tdims = _trajectory_inputs()
+    rows, pairs = [], 0
+    for f in range(5):
+        xf, Qf = frame(f)
+        r, st = f64.topo_batch(tseeds, tn_iter, xf, Qf, 0.1, tdims)
+        rows.append(r.astype(np.float32))
+        pairs += int((st.astype(np.int64) + 2).sum()) * len(Qf)
+    d_range, c_range, nd, nc = calc.bin_plan(rows)
+    want_counts = np.stack([np.histogram2d(r[:, 0].astype(np.float64), r[:, 1].astype(np.float64), bins=[nd, nc],
+                                           range=[d_range, c_range])[0].astype(np.int64) for r in rows])
+    want_h = want_counts.reshape(5, -1).astype(np.float64)
+    want_h = want_h / want_h.sum(axis=1, keepdims=True)
+    for r in range(2):
+        z = np.load(tmp_path / f"traj{r}.npz")
+        np.testing.assert_array_equal(z["plan"], np.array([*d_range, *c_range, nd, nc]))
+        np.testing.assert_array_equal(z["counts"], want_counts)
+        np.testing.assert_array_equal(z["hists"], want_h)
+        np.testing.assert_allclose(z["distance"], ohist.chi2_matrix(want_h), rtol=1e-13, atol=0)
+        assert int(z["pairs"][0]) * (1 if r else 1) > 0
+    assert int(np.load(tmp_path / "traj0.npz")["pairs"][0]) + int(np.load(tmp_path / "traj1.npz")["pairs"][0]) == pairs
