@@ -182,7 +182,10 @@ int cpet_topo_hist(cpet_ctx *ctx, int n_lines, const float *seeds, const int32_t
  * when n_iter_frame_stride != 0, its own n_iter row at n_iter + f*n_iter_frame_stride (0 = one row
  * shared by all frames).  counts is (n_frames,nd,nc) int64; out_rows is (n_frames,n_lines,2) f32 or
  * NULL.  Frames alternate between two internal streams, so the host<->device copies of one frame
- * overlap the kernels of its neighbours; pass pinned host memory for that overlap to be real.
+ * overlap the kernels of its neighbours.  Result buffers (and a per-frame n_iter table) that the caller left
+ * pageable are page-locked with cudaHostRegister for the duration of the call and released before it returns
+ * (tuning key "frames_pin", default 1), because a copy into pageable memory would block the enqueueing thread
+ * until the frame has finished; buffers that are already pinned are used as they are.
  * Every frame's result is identical to a cpet_topo_hist call on that frame alone. */
 int cpet_topo_hist_frames(cpet_ctx *ctx, int n_frames, const int *n_charges, const float *const *x,
                           const float *const *Q, int n_lines, const float *seeds,

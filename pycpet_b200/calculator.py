@@ -237,8 +237,15 @@ def make_histograms_from_arrays(topologies, plan=None):
     """Histograms of a list of (n_i,2) [dist|curv] arrays -> (F, nd*nc) float64, each row
     a/a.sum() flattened row-major (UC:702-713).  Frames of equal length go to the GPU as one
     batched launch; ragged frames one launch each."""
-    d_range, c_range, nd, nc = plan if plan is not None else bin_plan(topologies)
     tops = [np.ascontiguousarray(t, dtype=np.float64).reshape(-1, 2) for t in topologies]
+    if plan is None:
+        # .top values are float32 results printed with %.18e (CPET.py:123), so the float64 the reference parses
+        # are float32-exact: the global min / max / quartiles then come from the device radix select
+        # (bin_plan_device == bin_plan bit for bit); anything else keeps the reference's host rule
+        t32 = [t.astype(np.float32) for t in tops]
+        exact = all(np.array_equal(a.astype(np.float64), t) for a, t in zip(t32, tops))
+        plan = bin_plan_device(t32) if exact and sum(len(t) for t in tops) > 0 else bin_plan(topologies)
+    d_range, c_range, nd, nc = plan
     lens = {len(t) for t in tops}
     if len(lens) == 1:
         counts = histogram2d_counts(np.stack(tops), nd, nc, d_range, c_range)

@@ -227,6 +227,7 @@ int cpet_set_tuning(cpet_ctx* c, const char* key, int value) {
         {"k2_threads", &t.k2_threads}, {"k2_tile_pairs", &t.k2_tile_pairs},
         {"k2_stages", &t.k2_stages}, {"k2_sort", &t.k2_sort}, {"k2_cap", &t.k2_cap},
         {"k2_form", &t.k2_form}, {"k2_amax", &t.k2_amax}, {"k2_unroll", &t.k2_unroll},
+        {"frames_pin", &t.frames_pin},
         {"timing", &t.timing},
     };
     for (auto& e : tab) {
@@ -608,6 +609,25 @@ int cpet_topo_hist(cpet_ctx* c, int n_lines, const float* seeds, const int32_t* 
 }
 
 // ---------------------------------------------------------------- MD-frame batch -----------
+// Page-locks a caller's pageable host range for the lifetime of the object.  A device-to-host cudaMemcpyAsync into
+// pageable memory blocks the calling thread until the copy is done, i.e. until the frame's kernels have finished,
+// so frame f + 1 would not even be enqueued before frame f has completed and the second stream would buy nothing
+// for callers that pass plain NumPy arrays (the reference's own calling convention: np.zeros outputs).
+struct ScopedHostPin {
+    void* p = nullptr;
+    ScopedHostPin(void* ptr, size_t bytes, bool enable) {
+        if (!enable || !ptr || bytes < (1u << 16)) return;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return; }
+        if (a.type != cudaMemoryTypeUnregistered) return;              // already page-locked (or not host memory)
+        if (cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess) p = ptr;
+        else cudaGetLastError();                                        // not registrable: stay pageable
+    }
+    ~ScopedHostPin() { if (p) cudaHostUnregister(p); }
+    ScopedHostPin(const ScopedHostPin&) = delete;
+    ScopedHostPin& operator=(const ScopedHostPin&) = delete;
+};
+
 int cpet_topo_hist_frames(cpet_ctx* c, int n_frames, const int* n_charges, const float* const* x,
                           const float* const* Q, int n_lines, const float* seeds, const int32_t* n_iter,
                           int64_t n_iter_frame_stride, float step_size, const float dims[3], unsigned flags,
@@ -658,6 +678,14 @@ int cpet_topo_hist_frames(cpet_ctx* c, int n_frames, const int* n_charges, const
         return rc;
     }
     int64_t launches = 0;
+    // result buffers the caller left pageable are page-locked for the call (both streams are drained before the
+    // destructors run), so that the copies back really are asynchronous and neighbouring frames overlap
+    const bool pin = c->tune.frames_pin != 0 && n_frames > 1;
+    ScopedHostPin pin_rows(out_rows, out_rows ? sizeof(float) * 2 * n * (size_t)n_frames : 0, pin && n_lines > 0);
+    ScopedHostPin pin_counts(counts, cbytes * (size_t)n_frames, pin);
+    ScopedHostPin pin_iter(const_cast<int32_t*>(n_iter),
+                           n_iter_frame_stride ? sizeof(int32_t) * (size_t)n_iter_frame_stride * (size_t)n_frames : 0,
+                           pin && n_lines > 0);
     // every frame's work is enqueued asynchronously; whatever happens, both streams are drained before
     // this call returns, because the copies reference the caller's host buffers
     auto enqueue = [&]() -> int {

@@ -62,7 +62,9 @@ def topology_trajectory(engine, n_frames, frame_charges, seeds, n_iter, step_siz
     L = int(seeds_d.shape[0])
     rows = rows_out if rows_out is not None else torch.empty((len(mine), L, 2), dtype=torch.float32, device=dev)
     fixed_n_iter = None
-    if not callable(n_iter):
+    if torch.is_tensor(n_iter):
+        fixed_n_iter = n_iter.to(device=dev, dtype=torch.int32)
+    elif not callable(n_iter):
         fixed_n_iter = torch.as_tensor(np.asarray(n_iter).astype(np.int32)).to(dev)
     t = {}
 

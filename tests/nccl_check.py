@@ -70,6 +70,22 @@ def main():
         lambda ids: m.topo_hist_frames([frame_charges(f) for f in ids], seeds[:4096], n_iter[:4096],
                                        np.linspace(0, 1.8, 51), np.linspace(0, 5, 51), step_size=0.1,
                                        dimensions=dims)[1], 6)
+    # a box mesh by slabs of x-planes (lattice kernel per slab) -> all_gather
+    ax = torch.linspace(-0.5, 0.5, 43, device="cuda")
+    eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
+    esp = sharding.lattice_sharded(lambda xs, ys, zs: eng.esp_lattice(xs, ys, zs, concat_half=True), ax, ax, ax)
+    # exact global order statistics of the lines spread over the ranks (radix select, all-reduce per pass)
+    n_all = len(seeds)
+    want_ranks = [0, n_all // 4, n_all // 2, (3 * n_all) // 4, n_all - 1]
+    stats = [sharding.order_stats_sharded(lambda pre, bits, c=c: eng.radix_hist(mine, c, pre, bits), want_ranks)
+             for c in (0, 1)]
+    # the device-resident trajectory pipeline: 11 frames over the ranks, global bin plan, gathered counts,
+    # chi^2 row blocks
+    from pycpet_b200 import trajectory
+    def traj_frame(f):
+        xf, q = frame_charges(f)
+        return torch.from_numpy(xf).cuda(), torch.from_numpy(q).cuda()
+    tr = trajectory.topology_trajectory(eng, 11, traj_frame, seeds[:4096], n_iter[:4096], 0.1, dims)
     torch.cuda.synchronize()
 
     ok = True
@@ -88,6 +104,26 @@ def main():
             "frames gather": torch.equal(frames.to(fr1.device).to(fr1.dtype), fr1),
             "frames batch call + gather": torch.equal(batch.to(fr1.device).to(fr1.dtype).reshape(fr1.shape), fr1),
         }
+        eng.set_tuning(k1_lanes=0, k1_splits=0)
+        eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
+        esp1 = eng.esp_lattice(ax, ax, ax, concat_half=True)
+        d = (esp1[:, 3].float() - esp[:, 3].float()).abs().max() / esp1[:, 3].float().abs().max()
+        checks["lattice slabs all_gather (coordinates exact, phi within one float16 ulp)"] = (
+            torch.equal(esp1[:, :3], esp[:, :3]) and float(d) <= 1.5e-3)
+        srt = [torch.sort(t1[:, c]).values.cpu().numpy() for c in (0, 1)]
+        checks["order statistics over ranks"] = all(
+            np.array_equal(stats[c], srt[c][want_ranks]) for c in (0, 1))
+        # the same trajectory on one GPU, through the host-side plan
+        from pycpet_b200 import calculator as calc
+        rows1 = []
+        for f in range(11):
+            eng.set_charges(*traj_frame(f))
+            rows1.append(eng.topo_batch(torch.from_numpy(seeds[:4096]).cuda(), n_iter[:4096], 0.1, dims).cpu().numpy())
+        plan1 = calc.bin_plan([r.astype(np.float64) for r in rows1])
+        h1 = calc.make_histograms_from_arrays(rows1, plan=plan1)
+        checks["trajectory: bin plan == host plan"] = tr["plan"] == plan1
+        checks["trajectory: histograms"] = np.array_equal(tr["hists"].cpu().numpy(), h1)
+        checks["trajectory: chi2 matrix"] = np.array_equal(tr["distance"].cpu().numpy(), eng.chi2_rows(torch.from_numpy(h1).cuda()).cpu().numpy())
         for k, v in checks.items():
             print(f"[nccl_check world={world}] {k}: {'OK' if v else 'MISMATCH'}")
             ok = ok and v
