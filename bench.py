@@ -768,7 +768,7 @@ def run_split(args, rank, world, local_rank):
         eng.set_charges(dx, dq)
         if kind == "topo":
             one = eng.topo_batch(torch.from_numpy(seeds).to(dev), torch.from_numpy(n_iter).to(dev), prm["h"], dims)
-            ok = bool(torch.equal(one, full)) and bool(torch.equal(eng.hist2d(one, de, ce), dcounts))
+            ok = bool(torch.equal(one, full)) and bool(torch.equal(eng.hist2d(one, de, ce), dcounts[0]))
             what = "gathered rows (seed order) and histogram == the unsharded single-GPU run of the same frame, bit for bit"
         else:
             # the launcher's charge-range splits depend on the slab size, so the FP64 partial sums meet in another

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libcpetb200.so")
-SOURCES = ["capi.cu", "field.cu", "topo.cu", "hist.cu", "legacy.cu", "textio.cu"]
+SOURCES = ["capi.cu", "field.cu", "topo.cu", "topo8.cu", "hist.cu", "legacy.cu", "textio.cu"]
 HEADERS = ["common.cuh", "cpet_internal.h", os.path.join("..", "..", "include", "cpet_b200.h")]
 
 NVCC_FLAGS = [

@@ -371,6 +371,80 @@ __device__ __forceinline__ void evalx_near(const V16 v0, const V16 v1, XRegs<P>&
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Streamline kernel, points-packed hybrid form (topo8.cu, k2p_topo_kernel).
+//
+// The same two arithmetic forms, with the roles of the packed halves swapped: a packed register holds TWO
+// POINTS of the warp and a lane takes ONE charge per step, whose record is consumed through 32-bit broadcast
+// operands (FFMA2 R, R.F32x2, R.F32, R.F32x2).  The instruction count is unchanged (10 per two
+// pair-evaluations in the far form); what changes is the register-file traffic per instruction: no FFMA2 of the
+// far loop reads three distinct 64-bit registers any more (4 of 10 did), which is what held the charge-pair
+// form at 73.7 % of the FP32 peak in the loop microbenchmark against 79.0 % for this one
+// (tools/ubench2.cu X10 / XP10, profiles/round2_ubench2.txt).  A warp carries 8 points (4 packed pairs).
+//   far  record (24 B): a = {alpha x, alpha y, alpha z, alpha} (LDS.128), bb = {b, b} (LDS.64), b = alpha |x|^2
+//   near record       : a = {2x, 2y, 2z, 4q}
+// ------------------------------------------------------------------------------------------
+struct __align__(16) PBlock { float4 a[32]; float2 bb[32]; };
+static_assert(sizeof(PBlock) == 768, "points-packed charge block must be 768 bytes");
+
+struct PRegs {
+    u64 c0[4], c1[4], c2[4], c3[4];     // {-2p.x}, {-2p.y}, {-2p.z}, {|p|^2} of the point pair (positions 2j, 2j+1)
+    u64 a0[4], a1[4], a2[4], a3[4];     // FP32 partials per position: T.x - E_near.x, T.y - .., T.z - .., S
+};
+
+template <int NP>
+__device__ __forceinline__ void evalp_far(const float4 a, const u64 bb, PRegs& r) {
+    const u64 ax = pk2(a.x, a.x), ay = pk2(a.y, a.y), az = pk2(a.z, a.z), al = pk2(a.w, a.w);   // .F32 operands
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        u64 t = fma2(r.c3[p], al, bb);
+        t = fma2(ax, r.c0[p], t);
+        t = fma2(ay, r.c1[p], t);
+        t = fma2(az, r.c2[p], t);
+        const u64 inv = rsqrt2_abs(t);
+        const u64 u = mul2(mul2(inv, inv), inv);
+        r.a3[p] = fma2(u, al, r.a3[p]);
+        r.a0[p] = fma2(u, ax, r.a0[p]);
+        r.a1[p] = fma2(u, ay, r.a1[p]);
+        r.a2[p] = fma2(u, az, r.a2[p]);
+    }
+}
+
+template <int NP>
+__device__ __forceinline__ void evalp_near(const float4 a, PRegs& r) {
+    const u64 x2 = pk2(a.x, a.x), y2 = pk2(a.y, a.y), z2 = pk2(a.z, a.z), q4 = pk2(a.w, a.w);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const u64 dx = add2(r.c0[p], x2);          // -2 (p - x), exact
+        const u64 dy = add2(r.c1[p], y2);
+        const u64 dz = add2(r.c2[p], z2);
+        u64 r2 = mul2(dx, dx);
+        r2 = fma2(dy, dy, r2);
+        r2 = fma2(dz, dz, r2);
+        const u64 inv = rsqrt2(r2);
+        const u64 s = mul2(mul2(inv, inv), mul2(inv, q4));
+        r.a0[p] = fma2(s, dx, r.a0[p]);
+        r.a1[p] = fma2(s, dy, r.a1[p]);
+        r.a2[p] = fma2(s, dz, r.a2[p]);
+    }
+}
+
+// kappa = |v' x v''| / |v'|^3 from three consecutive FP32 positions, evaluated the way
+// math_module.c does (C:575-580 differences in float; C:89-96, 108-121 norms through double).
+__device__ __forceinline__ float curv3_f32(float3 a0, float3 a1, float3 a2) {
+    const float v1x = a1.x - a0.x, v1y = a1.y - a0.y, v1z = a1.z - a0.z;
+    const float v2x = a2.x - 2.0f * a1.x + a0.x;
+    const float v2y = a2.y - 2.0f * a1.y + a0.y;
+    const float v2z = a2.z - 2.0f * a1.z + a0.z;
+    const float cx = v1y * v2z - v1z * v2y;
+    const float cy = v1z * v2x - v1x * v2z;
+    const float cz = v1x * v2y - v1y * v2x;
+    const float nc = (float)sqrt((double)cx * cx + (double)cy * cy + (double)cz * cz);
+    const float nd = (float)sqrt((double)v1x * v1x + (double)v1y * v1y + (double)v1z * v1z);
+    const double d3 = (double)nd * (double)nd * (double)nd;
+    return (float)((double)nc / d3);
+}
+
 __device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask) {
     int lo = __double2loint(v), hi = __double2hiint(v);
     lo = __shfl_xor_sync(0xffffffffu, lo, lane_mask);

@@ -48,8 +48,9 @@ struct Tuning {
     int k1_softscan = -1;  // lattice kernel: -1 auto (scan for charges on grid nodes when the mesh is large), 0 off, 1 on
     int k2_threads = 0, k2_tile_pairs = 0, k2_stages = 0;
     int k2_sort = -1;   // -1 heuristic (on), 0 off, 1 on
-    int k2_cap = 0;     // streamlines per warp (1, 2, 4; 0 = heuristic)
-    int k2_form = 0;    // 0 = hybrid near/far kernel (default), 1 = round-1 direct-form kernel
+    int k2_cap = 0;     // streamlines per warp (1, 2, 4; 8 in the points-packed kernel; 0 = heuristic)
+    int k2_form = 0;    // 0 = auto (points-packed hybrid kernel, charge-pair-packed hybrid for short queues),
+                        // 1 = round-1 direct-form kernel, 2 = charge-pair-packed hybrid, 3 = points-packed hybrid
     int k2_unroll = 0;  // hybrid kernel: far-loop unroll of the 4-point pass (3, 4 or 6; 0 = 3)
     int k2_amax = 0;    // hybrid kernel: largest rounding amplification a far charge may have (0 = 8)
     int frames_pin = 1; // cpet_topo_hist_frames: page-lock pageable result buffers for the call (0 = leave them pageable)
@@ -106,6 +107,21 @@ int detect_lattice(cpet_ctx* c, int n_points, const float* d_x0, int* is_lattice
 // K2
 int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d_n_iter,
                 float step, const float dims[3], unsigned flags, float* d_out, int32_t* d_steps);
+
+// K2 internals shared by the streamline kernels (topo.cu, topo8.cu)
+struct K2XMeta {
+    unsigned ext[3];                 // max |seed coordinate| per axis, float bits
+    int n_near, n_far;               // charges per class
+    int nb_near, nb_far;             // blocks per class, in array order
+    int nb_total;
+};
+int prepare_queue(cpet_ctx* c, int n_lines, const int32_t* d_n_iter, bool do_sort, unsigned int** queue,
+                  unsigned long long** evals, const int32_t** order, int* launches);
+int pack_hybrid(cpet_ctx* c, int n_lines, const float* d_seeds, float step, const float dims[3], int layout,
+                int max_blocks, K2XMeta** meta_out, int* launches);
+bool topo8_wants(cpet_ctx* c, int n_lines);
+int launch_topo_points_packed(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d_n_iter, float step,
+                              const float dims[3], unsigned flags, float* d_out, int32_t* d_steps);
 
 // K3
 int launch_hist2d(cpet_ctx* c, int n_frames, int64_t n_per_frame, const void* d_values,

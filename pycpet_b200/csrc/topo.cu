@@ -34,22 +34,6 @@ namespace cpet {
 #endif                          // register-rotation MOVs per 160 packed instructions of the loop (10 at 384), measured
                                 // 2.49e12 against 2.59e12 pair-evals/s on the 3A frame (profiles/round2_k2x.md)
 
-// kappa = |v' x v''| / |v'|^3 from three consecutive FP32 positions, evaluated the way
-// math_module.c does (C:575-580 differences in float; C:89-96, 108-121 norms through double).
-__device__ __forceinline__ float curv3_f32(float3 a0, float3 a1, float3 a2) {
-    const float v1x = a1.x - a0.x, v1y = a1.y - a0.y, v1z = a1.z - a0.z;
-    const float v2x = a2.x - 2.0f * a1.x + a0.x;
-    const float v2y = a2.y - 2.0f * a1.y + a0.y;
-    const float v2z = a2.z - 2.0f * a1.z + a0.z;
-    const float cx = v1y * v2z - v1z * v2y;
-    const float cy = v1z * v2x - v1x * v2z;
-    const float cz = v1x * v2y - v1y * v2x;
-    const float nc = (float)sqrt((double)cx * cx + (double)cy * cy + (double)cz * cz);
-    const float nd = (float)sqrt((double)v1x * v1x + (double)v1y * v1y + (double)v1z * v1z);
-    const double d3 = (double)nd * (double)nd * (double)nd;
-    return (float)((double)nc / d3);
-}
-
 // 1/sqrt(a) and sqrt(a) in double from one MUFU.RSQ seed + two Newton steps (relative error
 // ~1e-15 after the second step) instead of the ~60-instruction software DSQRT/DDIV sequences: the
 // per-round state update is executed by every lane and sits on the critical path of each round.
@@ -436,13 +420,6 @@ __global__ void __launch_bounds__(CPET_K2_MAXT, 1) k2w_topo_kernel(const K2WPara
 // All three are O(M + L) and run on the launch stream; nothing is read back by the host (the
 // integrator takes the block counts from device memory).
 // =============================================================================================
-struct K2XMeta {
-    unsigned ext[3];                 // max |seed coordinate| per axis, float bits
-    int n_near, n_far;               // charges per class
-    int nb_near, nb_far;             // blocks per class, in array order
-    int nb_total;
-};
-
 #define K2X_CHUNK 1024               // charges per CTA of the packers
 
 __global__ void __launch_bounds__(256) k2x_extent_kernel(const float* __restrict__ seeds, int n_lines,
@@ -542,11 +519,38 @@ __device__ __forceinline__ void k2x_store_class(XBlock* __restrict__ out, int cl
     }
 }
 
+// The same records in the layout of the points-packed kernel (topo8.cu): 32 charges per PBlock,
+//   far : a = {alpha x, alpha y, alpha z, alpha}   bb = {b, b}      (b = alpha |x|^2, duplicated: it is the 64-bit
+//   near: a = {2x, 2y, 2z, 4q}                     bb unused         addend of the first FFMA2 of a point pair)
+__device__ __forceinline__ void k2p_store_class(PBlock* __restrict__ out, int cls, int first_block, int slot,
+                                                float x, float y, float z, float q, bool pad) {
+    PBlock& blk = out[first_block + (slot >> 5)];
+    const int l = slot & 31;
+    if (cls == 0) {
+        blk.a[l] = pad ? make_float4(2.0f * CPET_PAD_COORD, 2.0f * CPET_PAD_COORD, 2.0f * CPET_PAD_COORD, 0.f)
+                       : make_float4(2.0f * x, 2.0f * y, 2.0f * z, 4.0f * q);
+        blk.bb[l] = make_float2(0.f, 0.f);
+    } else if (pad || q == 0.f) {
+        blk.a[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+        blk.bb[l] = make_float2(CPET_X_PAD_B, CPET_X_PAD_B);
+    } else {
+        const double al = (q < 0.f ? -1.0 : 1.0) / ((double)q * (double)q);   // the record carries the sign of q
+        const double x2 = (double)x * x + (double)y * y + (double)z * z;
+        blk.a[l] = make_float4((float)(al * x), (float)(al * y), (float)(al * z), (float)al);
+        const float b = (float)(al * x2);
+        blk.bb[l] = make_float2(b, b);
+    }
+}
+
+template <int LAYOUT>      // 0: XBlock (64 charges, charge pairs packed), 1: PBlock (32 charges, one per lane)
 __global__ void __launch_bounds__(K2X_CHUNK) k2x_scatter_kernel(const ChargePair* __restrict__ pairs, int n_charges,
                                                                 float dx, float dy, float dz, float h, float amax,
                                                                 K2XMeta* __restrict__ meta,
                                                                 const int* __restrict__ chunk_counts, int n_chunks,
-                                                                XBlock* __restrict__ out) {
+                                                                void* __restrict__ out_raw) {
+    constexpr int SH = LAYOUT == 0 ? 6 : 5;          // log2(charges per block)
+    XBlock* out = reinterpret_cast<XBlock*>(out_raw);
+    PBlock* outp = reinterpret_cast<PBlock*>(out_raw);
     __shared__ int s_red[32][4];
     __shared__ int s_pre[2], s_tot[2];
     __shared__ int s_warp[32][2];
@@ -593,16 +597,22 @@ __global__ void __launch_bounds__(K2X_CHUNK) k2x_scatter_kernel(const ChargePair
         for (int j = 0; j < 32; ++j) { const int n = s_warp[j][k]; s_warp[j][k] = run; run += n; }
     }
     __syncthreads();
-    const int nb0 = (s_tot[0] + 63) >> 6, nb1 = (s_tot[1] + 63) >> 6;
+    const int nb0 = (s_tot[0] + (1 << SH) - 1) >> SH, nb1 = (s_tot[1] + (1 << SH) - 1) >> SH;
     const int first[2] = {0, nb0};
-    if (cls >= 0) k2x_store_class(out, cls, first[cls], s_pre[cls] + s_warp[w][cls] + rank, x, y, z, q, false);
+    if (cls >= 0) {
+        const int slot = s_pre[cls] + s_warp[w][cls] + rank;
+        if (LAYOUT == 0) k2x_store_class(out, cls, first[cls], slot, x, y, z, q, false);
+        else k2p_store_class(outp, cls, first[cls], slot, x, y, z, q, false);
+    }
     if (blockIdx.x == 0) {
         // zero-weight padding up to a whole block per class, and the counts the integrator reads
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int nb = k == 0 ? nb0 : nb1;
-            for (int slot = s_tot[k] + tid; slot < nb * 64; slot += K2X_CHUNK)
-                k2x_store_class(out, k, first[k], slot, 0.f, 0.f, 0.f, 0.f, true);
+            for (int slot = s_tot[k] + tid; slot < (nb << SH); slot += K2X_CHUNK) {
+                if (LAYOUT == 0) k2x_store_class(out, k, first[k], slot, 0.f, 0.f, 0.f, 0.f, true);
+                else k2p_store_class(outp, k, first[k], slot, 0.f, 0.f, 0.f, 0.f, true);
+            }
         }
         if (tid == 0) {
             meta->n_near = s_tot[0]; meta->n_far = s_tot[1];
@@ -1044,7 +1054,7 @@ __global__ void __launch_bounds__(256) k2_scatter_kernel(const int32_t* __restri
 
 // queue order (LPT): line ids sorted by n_iter descending into c->work1; leaves `order` null when
 // the sort is skipped.  Also zeroes the queue cursor / evaluation counter block.
-static int prepare_queue(cpet_ctx* c, int n_lines, const int32_t* d_n_iter, bool do_sort,
+int prepare_queue(cpet_ctx* c, int n_lines, const int32_t* d_n_iter, bool do_sort,
                          unsigned int** queue, unsigned long long** evals, const int32_t** order,
                          int* launches) {
     const int sms = c->sm_count;
@@ -1174,6 +1184,42 @@ static int launch_topo_warpwide(cpet_ctx* c, int n_lines, const float* d_seeds, 
     return CPET_OK;
 }
 
+// Seed extent, class of every charge (near / far against this launch's box) and stable compaction into the
+// blocks of `layout` (0 = XBlock, 1 = PBlock) in c->xblocks; nothing is read back by the host, the integrator
+// takes the block counts from *meta_out in device memory.  Must follow prepare_queue (which zeroes the meta).
+int pack_hybrid(cpet_ctx* c, int n_lines, const float* d_seeds, float step, const float dims[3], int layout,
+                int max_blocks, K2XMeta** meta_out, int* launches) {
+    const int sms = c->sm_count;
+    K2XMeta* meta = reinterpret_cast<K2XMeta*>(c->counters.as<unsigned char>() + 16);   // zeroed by prepare_queue
+    static_assert(sizeof(K2XMeta) <= 48, "K2XMeta must fit the counter block header");
+    const int n_chunks = (c->n_charges + K2X_CHUNK - 1) / K2X_CHUNK;
+    const size_t block_bytes = layout == 0 ? sizeof(XBlock) : sizeof(PBlock);
+    if (int rc = c->xblocks.reserve(block_bytes * (size_t)max_blocks)) return rc;
+    if (int rc = c->xchunks.reserve(sizeof(int) * 2 * (size_t)(n_chunks > 0 ? n_chunks : 1))) return rc;
+    const float amax = c->tune.k2_amax > 0 ? (float)c->tune.k2_amax : 8.0f;
+    int eb = (n_lines + 255) / 256;
+    if (eb > sms * 4) eb = sms * 4;
+    k2x_extent_kernel<<<eb, 256, 0, c->stream>>>(d_seeds, n_lines, meta);
+    *launches += 1;
+    if (n_chunks > 0) {
+        k2x_count_kernel<<<n_chunks, K2X_CHUNK, 0, c->stream>>>(c->charges.as<ChargePair>(), c->n_charges, dims[0],
+                                                               dims[1], dims[2], step, amax, meta,
+                                                               c->xchunks.as<int>());
+        if (layout == 0)
+            k2x_scatter_kernel<0><<<n_chunks, K2X_CHUNK, 0, c->stream>>>(c->charges.as<ChargePair>(), c->n_charges,
+                                                                        dims[0], dims[1], dims[2], step, amax, meta,
+                                                                        c->xchunks.as<int>(), n_chunks, c->xblocks.p);
+        else
+            k2x_scatter_kernel<1><<<n_chunks, K2X_CHUNK, 0, c->stream>>>(c->charges.as<ChargePair>(), c->n_charges,
+                                                                        dims[0], dims[1], dims[2], step, amax, meta,
+                                                                        c->xchunks.as<int>(), n_chunks, c->xblocks.p);
+        *launches += 2;
+    }
+    CPET_CUDA_TRY(cudaGetLastError());
+    *meta_out = meta;
+    return CPET_OK;
+}
+
 template <bool SD, int U4, int U2>
 static int launch_k2x_inst(cpet_ctx* c, const K2XParams& prm, int grid, int threads, size_t smem) {
     auto kern = k2x_topo_kernel<SD, U4, U2>;
@@ -1240,29 +1286,8 @@ static int launch_topo_hybrid(cpet_ctx* c, int n_lines, const float* d_seeds, co
         return rc;
 
     // --- classify and pack the charges against this launch's box ---------------------------------------
-    K2XMeta* meta = reinterpret_cast<K2XMeta*>(c->counters.as<unsigned char>() + 16);   // zeroed by prepare_queue
-    static_assert(sizeof(K2XMeta) <= 48, "K2XMeta must fit the counter block header");
-    const int n_chunks = (c->n_charges + K2X_CHUNK - 1) / K2X_CHUNK;
-    if (int rc = c->xblocks.reserve(sizeof(XBlock) * (size_t)max_blocks)) return rc;
-    if (int rc = c->xchunks.reserve(sizeof(int) * 2 * (size_t)(n_chunks > 0 ? n_chunks : 1))) return rc;
-    const float amax = tu.k2_amax > 0 ? (float)tu.k2_amax : 8.0f;
-    {
-        int eb = (n_lines + 255) / 256;
-        if (eb > sms * 4) eb = sms * 4;
-        k2x_extent_kernel<<<eb, 256, 0, c->stream>>>(d_seeds, n_lines, meta);
-        launches += 1;
-        if (n_chunks > 0) {
-            k2x_count_kernel<<<n_chunks, K2X_CHUNK, 0, c->stream>>>(c->charges.as<ChargePair>(), c->n_charges, dims[0],
-                                                                   dims[1], dims[2], step, amax, meta,
-                                                                   c->xchunks.as<int>());
-            k2x_scatter_kernel<<<n_chunks, K2X_CHUNK, 0, c->stream>>>(c->charges.as<ChargePair>(), c->n_charges,
-                                                                     dims[0], dims[1], dims[2], step, amax, meta,
-                                                                     c->xchunks.as<int>(), n_chunks,
-                                                                     c->xblocks.as<XBlock>());
-            launches += 2;
-        }
-        CPET_CUDA_TRY(cudaGetLastError());
-    }
+    K2XMeta* meta = nullptr;
+    if (int rc = pack_hybrid(c, n_lines, d_seeds, step, dims, 0, max_blocks, &meta, &launches)) return rc;
 
     prm.blocks = c->xblocks.as<XBlock>();
     prm.meta = meta;
@@ -1301,6 +1326,12 @@ int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d
     if (n_lines == 0) return CPET_OK;
     if (c->tune.k2_form == 1)   // the round-1 direct-form kernel, kept for A/B measurements
         return launch_topo_warpwide(c, n_lines, d_seeds, d_n_iter, step, dims, flags, d_out, d_steps);
+    if (c->tune.k2_form == 2)   // the charge-pair-packed hybrid kernel
+        return launch_topo_hybrid(c, n_lines, d_seeds, d_n_iter, step, dims, flags, d_out, d_steps);
+    // default: the points-packed hybrid kernel (topo8.cu) once every warp of the chip gets at least 4 lines; shorter
+    // queues keep the charge-pair-packed kernel, which fills a warp with one or two lines
+    if (c->tune.k2_form == 3 || topo8_wants(c, n_lines))
+        return launch_topo_points_packed(c, n_lines, d_seeds, d_n_iter, step, dims, flags, d_out, d_steps);
     return launch_topo_hybrid(c, n_lines, d_seeds, d_n_iter, step, dims, flags, d_out, d_steps);
 }
 

@@ -31,7 +31,9 @@ def main():
     # K1's launch heuristics depend on the shard size (lanes per point, charge splits), which changes
     # the order of the FP64 partial sums; pin them so sharded == unsharded bit for bit.  The streamline
     # kernel sums every line in the same order whatever the shard size.
-    eng.set_tuning(k1_lanes=8, k1_splits=1)
+    # Likewise the streamline kernel FORM follows the queue length (points-packed for long queues, charge-pair-
+    # packed for short ones); within a form every line is summed in the same order whatever the shard size.
+    eng.set_tuning(k1_lanes=8, k1_splits=1, k2_form=3)
     x, Q = synth.charges(7890, seed=1, box=0.5)
     eng.set_charges(torch.from_numpy(x).cuda(), torch.from_numpy(Q).cuda())
 

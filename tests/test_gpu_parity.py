@@ -490,6 +490,11 @@ def test_topo_example_3A(M, golden, frame2a):
 @pytest.mark.parametrize("cfg", [
     # lines per warp, charge residency, thread counts, queue order
     dict(), dict(k2_cap=1), dict(k2_cap=2), dict(k2_cap=4), dict(k2_cap=4, k2_threads=64, k2_sort=1),
+    dict(k2_form=2), dict(k2_form=2, k2_cap=4), dict(k2_form=2, k2_cap=4, k2_tile_pairs=256, k2_stages=2),   # charge-pair-packed hybrid
+    dict(k2_form=3), dict(k2_form=3, k2_cap=8), dict(k2_form=3, k2_cap=4), dict(k2_form=3, k2_cap=2),        # points-packed hybrid
+    dict(k2_form=3, k2_cap=1, k2_threads=64), dict(k2_form=3, k2_cap=8, k2_threads=32, k2_sort=0),
+    dict(k2_form=3, k2_cap=8, k2_tile_pairs=256, k2_stages=2), dict(k2_form=3, k2_tile_pairs=64, k2_stages=4, k2_unroll=4),
+    dict(k2_form=3, k2_unroll=8),
     dict(k2_cap=2, k2_sort=0), dict(k2_cap=4, k2_tile_pairs=256, k2_stages=2),   # streamed charge ring
     dict(k2_cap=1, k2_tile_pairs=64, k2_stages=4), dict(k2_cap=2, k2_tile_pairs=512, k2_stages=3, k2_threads=128),
 ])
@@ -615,7 +620,9 @@ def test_topo_hybrid_charge_classes(M, signs):
     seeds, n_iter, dims, _ = synth.seeds(9, 0.5, 0.1)
     want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
     for cfg in (dict(), dict(k2_amax=1), dict(k2_amax=100000), dict(k2_form=1), dict(k2_cap=1), dict(k2_cap=2),
-                dict(k2_tile_pairs=256, k2_stages=2)):
+                dict(k2_tile_pairs=256, k2_stages=2), dict(k2_form=3), dict(k2_form=3, k2_amax=1),
+                dict(k2_form=3, k2_amax=100000), dict(k2_form=3, k2_cap=8), dict(k2_form=3, k2_cap=1),
+                dict(k2_form=3, k2_tile_pairs=256, k2_stages=2), dict(k2_form=2)):
         reset_tuning(M)
         M.set_tuning(**cfg)
         M.set_charges(x, Q)
@@ -704,12 +711,24 @@ def test_topo_ragged_sizes(M, m_charges):
         if L == 2500:
             ref_rows = (seeds, n_iter, got)
     # the first 100 lines alone, and with 4 / 2 / 1 lines per warp: same bits as inside the big batch
+    # (2,500 lines are a short queue: the default form is the charge-pair-packed hybrid kernel)
     seeds, n_iter, got = ref_rows
     for cfg in (dict(), dict(k2_cap=4), dict(k2_cap=2), dict(k2_cap=1, k2_threads=96)):
         M.set_tuning(**cfg)
         sub = M.topo_batch(seeds[:100], n_iter[:100], step_size=0.1, dimensions=dims)
         np.testing.assert_array_equal(sub, got[:100])
         reset_tuning(M)
+    # the points-packed kernel: 8 / 4 / 2 / 1 lines per warp, whole batch or the first 100 lines: same bits
+    M.set_tuning(k2_form=3)
+    got3 = M.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims)
+    assert np.nanmax(np.abs(got3[:, 0] - got[:, 0])) <= 4e-6 or m_charges < 64
+    for cfg in (dict(), dict(k2_cap=8), dict(k2_cap=4), dict(k2_cap=2), dict(k2_cap=1, k2_threads=96),
+                dict(k2_cap=8, k2_threads=64)):
+        reset_tuning(M)
+        M.set_tuning(k2_form=3, **cfg)
+        sub = M.topo_batch(seeds[:100], n_iter[:100], step_size=0.1, dimensions=dims)
+        np.testing.assert_array_equal(sub, got3[:100])
+    reset_tuning(M)
 
 
 def test_topo_full_size_3A_properties(M, frame2a):
@@ -752,8 +771,11 @@ def test_config4_frame_of_one_million_seeds(M, frame2a):
     idx = np.random.default_rng(3).choice(len(seeds), 2048, replace=False)
     want, wsteps = f64.topo_batch(seeds[idx], n_iter[idx], x, Q, 0.1, dims)
     check_lines(got[idx], steps[idx], want, wsteps, 0.1, curv_tol_dir(0.1))
-    # a line's result does not depend on the batch it was computed in
+    # a line's result does not depend on the batch it was computed in (same kernel form: 2,048 lines alone would
+    # be a short queue and default to the charge-pair-packed kernel)
+    M.set_tuning(k2_form=3)
     sub = M.topo_batch(seeds[idx], n_iter[idx], x, Q, 0.1, dims)
+    reset_tuning(M)
     np.testing.assert_array_equal(sub, got[idx])
     # the direct-form kernel walks the same lines (a step-count flip needs a point within rounding of a box face)
     M.set_tuning(k2_form=1)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""A/B of the streamline kernel forms on the bench cases: k2_form=1 (round-1 direct form) against
-k2_form=0 (hybrid near/far), kernel time only (CUDA events around the integrator launch, best of 5),
+"""A/B of the streamline kernel forms on the bench cases: k2_form=1 (round-1 direct form), 2 (hybrid near/far,
+charge pairs packed) and 3 (hybrid, points packed: the default for long queues), kernel time only (CUDA events around the integrator launch, best of 5),
 plus the largest difference of the two outputs and both against the float64 oracle on a sample."""
 import json
 import os
@@ -32,7 +32,7 @@ def main():
         sample = np.random.default_rng(0).choice(len(seeds), size=min(256, len(seeds)), replace=False)
         ref, _ = f64.topo_batch(seeds[sample], n_iter[sample], x, Q, h, dims)
         outs = {}
-        for cfg in [dict(k2_form=1), dict(k2_form=0)] + extra:
+        for cfg in [dict(k2_form=1), dict(k2_form=2), dict(k2_form=3)] + extra:
             eng.set_tuning(k2_form=0, k2_threads=0, k2_cap=0, k2_amax=0, k2_unroll=0)
             eng.set_tuning(**cfg)
             best = 1e30
@@ -50,8 +50,8 @@ def main():
                                   dist_err=float(np.nanmax(d[:, 0])), curv_err=float(np.nanmax(d[:, 1])),
                                   launches=c["launches"])), flush=True)
         ks = list(outs)
-        dd = np.abs(outs[ks[0]] - outs[ks[1]])
-        print(json.dumps(dict(direct_vs_hybrid_max_dist=float(np.nanmax(dd[:, 0])), max_curv=float(np.nanmax(dd[:, 1])),
+        dd = np.abs(outs[ks[0]] - outs[ks[2]])
+        print(json.dumps(dict(direct_vs_points_packed_max_dist=float(np.nanmax(dd[:, 0])), max_curv=float(np.nanmax(dd[:, 1])),
                               lines_differing_by_a_step=int((dd[:, 0] > h / 2).sum()))), flush=True)
 
 

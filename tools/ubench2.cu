@@ -34,6 +34,22 @@ __device__ __forceinline__ u64 rsq2(u64 t) {
 
 template <int FORM, int P>
 __device__ __forceinline__ void eval(const V16 v0, const V16 v1, const u64 v2, Regs<FORM, P>& r) {
+    if (FORM == 9 || FORM == 10 || FORM == 11) {
+        // XP10: P points in P/2 packed pairs; ONE charge per lane and step: v0 = {x,y,z,|x|^2}, v1 = {q,qx,qy,qz};
+        // c0..2 = {-2p} packed over the two points, c3 = {|p|^2}; every charge operand is a .F32 broadcast
+        float x, y, z, x2, q, qx, qy, qz;
+        upk2(v0.a, x, y); upk2(v0.b, z, x2); upk2(v1.a, q, qx); upk2(v1.b, qy, qz);
+#pragma unroll
+        for (int p = 0; p < P / 2; ++p) {
+            u64 t = add2(r.c3[p], pk2(x2, x2));
+            t = fma2(pk2(x, x), r.c0[p], t); t = fma2(pk2(y, y), r.c1[p], t); t = fma2(pk2(z, z), r.c2[p], t);
+            const u64 inv = (FORM == 10) ? t : rsq2(t);
+            const u64 u = mul2(mul2(inv, inv), inv);
+            r.a3[p] = fma2(u, pk2(q, q), r.a3[p]);
+            r.a0[p] = fma2(u, pk2(qx, qx), r.a0[p]); r.a1[p] = fma2(u, pk2(qy, qy), r.a1[p]); r.a2[p] = fma2(u, pk2(qz, qz), r.a2[p]);
+        }
+        return;
+    }
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         if (FORM == 0 || FORM == 6) {           // D12: v0 = {-x,-y}, v1 = {-z,q}; c0..2 = p
@@ -85,7 +101,14 @@ __global__ void __launch_bounds__(T, 1) kLoop(const UBlock* __restrict__ g, int 
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const float x = px + 0.01f * p, y = py - 0.02f * p, z = pz + 0.03f * p;
-            if (FORM == 0 || FORM == 6) { r.c0[p] = pk2(x, x); r.c1[p] = pk2(y, y); r.c2[p] = pk2(z, z); r.c3[p] = 0ull; }
+            if (FORM == 9 || FORM == 10 || FORM == 11) {
+                if (p < P / 2) {
+                    const float x1 = x + 0.005f, y1 = y + 0.007f, z1 = z - 0.004f;
+                    r.c0[p] = pk2(-2 * x, -2 * x1); r.c1[p] = pk2(-2 * y, -2 * y1); r.c2[p] = pk2(-2 * z, -2 * z1);
+                    r.c3[p] = pk2(x * x + y * y + z * z, x1 * x1 + y1 * y1 + z1 * z1);
+                }
+            }
+            else if (FORM == 0 || FORM == 6) { r.c0[p] = pk2(x, x); r.c1[p] = pk2(y, y); r.c2[p] = pk2(z, z); r.c3[p] = 0ull; }
             else if (FORM == 7 || FORM == 8) {
                    const float e = seed * 1e-7f;   // halves differ: ptxas cannot use the .F32 broadcast operand form
                    r.c0[p] = pk2(-2 * x, -2 * x + e); r.c1[p] = pk2(-2 * y, -2 * y + e); r.c2[p] = pk2(-2 * z, -2 * z + e);
@@ -96,11 +119,11 @@ __global__ void __launch_bounds__(T, 1) kLoop(const UBlock* __restrict__ g, int 
         }
 #pragma unroll U
         for (int b = 0; b < nblk; ++b) {
-            const int bi = (FORM == 5 || FORM == 6) ? first_only : b;   // 5/6: loop-invariant loads (no LDS in the loop)
+            const int bi = (FORM == 5 || FORM == 6 || FORM == 11) ? first_only : b;   // 5/6: loop-invariant loads (no LDS in the loop)
             const V16 v0 = blk[bi].v0[lane];
             const V16 v1 = blk[bi].v1[lane];
             u64 v2 = 0ull;
-            if (FORM != 0 && FORM != 6) v2 = blk[bi].v2[lane];
+            if (FORM != 0 && FORM != 6 && FORM < 9) v2 = blk[bi].v2[lane];
             eval<FORM, P>(v0, v1, v2, r);
         }
 #pragma unroll
@@ -142,7 +165,7 @@ static int run(const char* name, const UBlock* g, int nblk, int sms, float* sink
     const int passes = 400;
     const float ms = time_kernel([&] { kern<<<sms, T, smem>>>(g, nblk, passes, 0.013f, sink); });
     CK(cudaGetLastError());
-    const double pe = (double)sms * (T / 32) * passes * (double)nblk * 32 * 2 * P;
+    const double pe = (double)sms * (T / 32) * passes * (double)nblk * 32 * (FORM >= 9 ? 1 : 2) * P;
     printf("%-5s P=%d U=%d T=%3d regs=%3d : %.3e pair-evals/s (%.1f%% of 3.7225e12)\n", name, P, U, T, fa.numRegs,
            pe / (ms * 1e-3), pe / (ms * 1e-3) / 3.7225e12 * 100);
     return 0;
@@ -178,6 +201,8 @@ int main(int argc, char** argv) {
         R(3, 4, 4, 384, "X10F") R(3, 4, 2, 384, "X10F") R(3, 4, 4, 512, "X10F")
         R(2, 2, 4, 512, "X10") R(2, 2, 4, 768, "X10") R(2, 3, 4, 512, "X10")
         R(0, 2, 4, 768, "D12") R(1, 2, 4, 768, "X11")
+        R(9, 8, 4, 384, "XP10") R(9, 8, 4, 512, "XP10") R(9, 8, 8, 384, "XP10") R(9, 8, 2, 512, "XP10") R(9, 4, 8, 512, "XP10")
+        R(9, 8, 6, 384, "XP10") R(10, 8, 4, 384, "XP10noMUFU") R(11, 8, 4, 384, "XP10noLDS") R(5, 4, 4, 512, "X10noLDS") R(6, 4, 4, 512, "D12noLDS")
         R(4, 4, 4, 512, "X10noMUFU") R(7, 4, 4, 512, "X10dup") R(8, 4, 4, 512, "X10dupnoMUFU") R(7, 4, 4, 384, "X10dup")
     }
     return 0;
