@@ -302,6 +302,7 @@ def run_gpu(args, rank, world, local_rank, sub=False):
                 c = eng.last_counters()
                 pool_pairs[j] = c["pair_evals"]
                 work["units"], work["k_launch"] = len(inp["seeds"]), c["launches"]
+                work["path"] = eng.last_path() if hasattr(eng, "last_path") else "k2p"
             eng.hist2d(dout, de, ce, out=dcounts)
             if probe:
                 pool_counts[j] = dcounts[0].clone()
@@ -568,7 +569,7 @@ def run_gpu(args, rank, world, local_rank, sub=False):
                             "max": [round(float(v), 4) for v in per_rank[:, 1]],
                             "kernel_mean": [round(float(v), 4) for v in per_rank[:, 2]]},
         "roofline": {"bound": "fp32-non-tensor" if kind != "esp" else "mufu (fp32 fraction quoted at 11 flop/pair)",
-                     "kernel": ("k2x_topo_kernel" if kind == "topo" else
+                     "kernel": (work.get("path", "k2p") + "_topo_kernel" if kind == "topo" else
                                 ("k1_lattice_kernel" if len(inp["points"]) >= 4096 else "k1_grid_kernel")),
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_source": "measured live: register-resident FMA loop (cpet_fp32_peak_probe, "
@@ -833,7 +834,7 @@ def run_split(args, rank, world, local_rank):
                              "wait for the slowest rank" if kind == "topo" else
                              "gather_ms = all_gather_into_tensor of the slabs, including the wait for the slowest rank")},
         "roofline": {"bound": "fp32-non-tensor" if kind != "esp" else "mufu (fp32 fraction quoted at 11 flop/pair)",
-                     "kernel": "k2x_topo_kernel" if kind == "topo" else "k1_lattice_kernel",
+                     "kernel": (eng.last_path() + "_topo_kernel") if kind == "topo" else "k1_lattice_kernel",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_nominal": achieved / NOMINAL_FP32_TFLOPS,
                      "flops_per_pair": flops, "kernel_ms": float(allr[0, 3]), "traffic": None},

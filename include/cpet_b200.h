@@ -60,7 +60,9 @@ int cpet_create_on_stream(int device, void *cuda_stream, cpet_ctx **out);
 int cpet_destroy(cpet_ctx *ctx);
 int cpet_sync(cpet_ctx *ctx);
 int cpet_device_of(cpet_ctx *ctx);
-/* Diagnostic: which K1 kernel served the last field/ESP call (0 general, 1 lattice). */
+/* Diagnostic: which kernel served the last call on this context.  Field / ESP: 0 general point-list kernel,
+ * 1 lattice kernel.  Streamlines: 11 direct-form kernel (k2w), 12 hybrid, charge pairs packed (k2x),
+ * 13 hybrid, points packed (k2p). */
 int cpet_last_path(cpet_ctx *ctx);
 /* Tuning knobs for experiments (the defaults are measured heuristics, profiles/round1_sweep.md):
  * "k1_threads","k1_points" (points or z-nodes per thread),"k1_lanes" (lanes per point: 1, 8, 32),

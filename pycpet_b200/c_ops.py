@@ -111,8 +111,8 @@ class Math_ops:
         return {"launches": int(out[0]), "pair_evals": int(out[1]), "field_evals": int(out[2])}
 
     def last_path(self) -> str:
-        """Which K1 kernel served the last field/ESP call: 'lattice' or 'general'."""
-        return "lattice" if self.math.cpet_last_path(self.ctx) == 1 else "general"
+        """Which kernel served the last call: "general" / "lattice" (field, ESP), "k2w" / "k2x" / "k2p" (streamlines)."""
+        return _lib.PATH_NAMES.get(int(self.math.cpet_last_path(self.ctx)), "general")
 
     def last_kernel_ms(self) -> float:
         ms = ctypes.c_double(0.0)

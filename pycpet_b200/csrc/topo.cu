@@ -1324,14 +1324,21 @@ int launch_topo(cpet_ctx* c, int n_lines, const float* d_seeds, const int32_t* d
     CPET_REQUIRE(c->charges_set, CPET_ERR_STATE, "no charge set on this context: call cpet_set_charges first");
     c->last_counters[0] = c->last_counters[1] = c->last_counters[2] = 0;
     if (n_lines == 0) return CPET_OK;
-    if (c->tune.k2_form == 1)   // the round-1 direct-form kernel, kept for A/B measurements
+    if (c->tune.k2_form == 1) { // the round-1 direct-form kernel, kept for A/B measurements
+        c->last_path = 11;
         return launch_topo_warpwide(c, n_lines, d_seeds, d_n_iter, step, dims, flags, d_out, d_steps);
-    if (c->tune.k2_form == 2)   // the charge-pair-packed hybrid kernel
+    }
+    if (c->tune.k2_form == 2) { // the charge-pair-packed hybrid kernel
+        c->last_path = 12;
         return launch_topo_hybrid(c, n_lines, d_seeds, d_n_iter, step, dims, flags, d_out, d_steps);
+    }
     // default: the points-packed hybrid kernel (topo8.cu) once every warp of the chip gets at least 4 lines; shorter
     // queues keep the charge-pair-packed kernel, which fills a warp with one or two lines
-    if (c->tune.k2_form == 3 || topo8_wants(c, n_lines))
+    if (c->tune.k2_form == 3 || topo8_wants(c, n_lines)) {
+        c->last_path = 13;
         return launch_topo_points_packed(c, n_lines, d_seeds, d_n_iter, step, dims, flags, d_out, d_steps);
+    }
+    c->last_path = 12;
     return launch_topo_hybrid(c, n_lines, d_seeds, d_n_iter, step, dims, flags, d_out, d_steps);
 }
 

@@ -66,6 +66,10 @@ class Engine:
         check(self.lib.cpet_last_counters(self.ctx, out))
         return {"launches": int(out[0]), "pair_evals": int(out[1]), "field_evals": int(out[2])}
 
+    def last_path(self) -> str:
+        """Which kernel served the last call: "general" / "lattice" (field, ESP), "k2w" / "k2x" / "k2p" (streamlines)."""
+        return _lib.PATH_NAMES.get(int(self.lib.cpet_last_path(self.ctx)), "general")
+
     def last_kernel_ms(self) -> float:
         ms = ctypes.c_double(0.0)
         check(self.lib.cpet_last_kernel_ms(self.ctx, ctypes.byref(ms)))

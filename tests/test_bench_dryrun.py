@@ -83,7 +83,7 @@ class FakeEngine:
         if out is None:
             out = torch.zeros((1, len(d_edges) - 1, len(c_edges) - 1), dtype=torch.int64)
         out.fill_(_frame_code(self.frame_tag))          # a frame's histogram depends on the frame only
-        return out
+        return out[0] if values.dim() == 2 else out     # like Engine.hist2d: (n, 2) values -> (nd, nc)
 
     def field_grid(self, x0, soften=True, concat=False, out=None):
         self.calls["grid"] += 1
@@ -116,6 +116,9 @@ class FakeEngine:
         else:
             out.fill_(1.0)
         return out
+
+    def last_path(self):
+        return "k2p"
 
     def last_counters(self):
         return {"launches": 4, "pair_evals": self._pairs(self.units), "field_evals": 0}
@@ -235,7 +238,7 @@ def test_topo_accounting_single_rank(bench_mod):
     assert line["gpu_launches"] == steps * (1 + 4 + 1)
     # roofline: 20 flop x mean pair-evals per timed step / the integrator's own duration
     r = line["roofline"]
-    assert r["kernel"] == "k2x_topo_kernel" and r["kernel_ms"] == pytest.approx(K_MS)
+    assert r["kernel"] == "k2p_topo_kernel" and r["kernel_ms"] == pytest.approx(K_MS)
     assert r["achieved"] == pytest.approx(want_pairs / steps * 20.0 / (K_MS * 1e-3) / 1e12)
     assert r["peak"] == 73.4 and r["frac"] == pytest.approx(r["achieved"] / 73.4)
     # end-to-end arm: one warm-up call and ONE timed call of `steps` frames, in the rotation of the device arm

@@ -26,12 +26,14 @@ for M_ in (301, 20_000):                       # resident and streamed charge st
     m.field_lattice(ax, ax, ax, soften=True)
     m.set_tuning(k1_softscan=-1)
     seeds, n_iter, dims, _ = synth.seeds(6, 0.5, 0.1)
-    for cfg in (dict(), dict(k2_cap=1), dict(k2_cap=2, k2_threads=128), dict(k2_cap=4, k2_tile_pairs=64, k2_stages=2)):
-        m.set_tuning(k2_cap=0, k2_threads=0, k2_tile_pairs=0, k2_stages=0)
+    for cfg in (dict(), dict(k2_cap=1), dict(k2_cap=2, k2_threads=128), dict(k2_cap=4, k2_tile_pairs=64, k2_stages=2),
+                dict(k2_form=1), dict(k2_form=2, k2_cap=4), dict(k2_form=3), dict(k2_form=3, k2_cap=8, k2_threads=64),
+                dict(k2_form=3, k2_cap=4, k2_tile_pairs=64, k2_stages=2), dict(k2_form=3, k2_cap=1)):
+        m.set_tuning(k2_cap=0, k2_threads=0, k2_tile_pairs=0, k2_stages=0, k2_form=0)
         m.set_tuning(**cfg)
         rows, steps = m.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, want_steps=True)
         m.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, second_diff=True)
-    m.set_tuning(k2_cap=0, k2_threads=0, k2_tile_pairs=0, k2_stages=0)
+    m.set_tuning(k2_cap=0, k2_threads=0, k2_tile_pairs=0, k2_stages=0, k2_form=0)
     de, ce = np.linspace(0, 1.8, 21), np.linspace(0, 5, 31)
     m.hist2d(rows, de, ce)
     m.topo_hist(seeds, n_iter, de, ce, step_size=0.1, dimensions=dims)
@@ -44,4 +46,10 @@ H = np.random.default_rng(1).random((5, 100)); H /= H.sum(1, keepdims=True)
 m.chi2_matrix(H)
 m.calc_field(np.zeros(3, np.float32), x, Q); m.calc_esp_base(np.zeros(3, np.float32), x, Q)
 m.thread_operation(seeds[0], 5, x, Q, 0.1, dims)
+import torch
+from pycpet_b200.device import Engine
+eng = Engine(0)
+eng.chi2_rows(torch.from_numpy(H).cuda(), 1, 3)
+eng.radix_hist(torch.from_numpy(rows).cuda(), 1, np.array([0], np.uint32), 0)
+torch.cuda.synchronize()
 print("sanitize target done")
