@@ -376,6 +376,7 @@ def run_gpu(args, rank, world, local_rank, sub=False):
         barrier()
         sampler.stop()
         kern_ms[:] = eng.kernel_times()  # dominant kernel alone, one entry per timed step
+        work["launches"] = launches["n"]  # kernels launched inside the timed region
         work["step_ms"] = [a.elapsed_time(b) for a, b in evs[:-1]]
         return sum(a.elapsed_time(b) for a, b in evs) * 1e-3
 
@@ -561,7 +562,7 @@ def run_gpu(args, rank, world, local_rank, sub=False):
                         if kind == "topo" else
                         "Math_ops.field_grid / esp_grid -> cpet_field_grid / cpet_esp_grid, one call per step, "
                         "pinned host buffers")},
-        "gpu_launches": int(launches["n"]),
+        "gpu_launches": int(work["launches"]),
         "parity_checked": bool(per_rank[:, 3].min() == 1.0) if kind == "topo" else None,
         "parity": ("; ".join(parity["what"]) if kind == "topo" else
                    "grid workloads: see tests/test_gpu_parity.py (oracle parity at this size)"),

@@ -226,7 +226,25 @@ struct LatticeRegs {
     u64 ax[PZ], ay[PZ], az[PZ];
 };
 
-template <int MODE, int PZ>
+// 1/sqrt of two values WITHOUT the special-function unit: integer seed on the ALU pipe (0x5f3759df - (bits >> 1),
+// 3.4 % off at most), three Newton steps y <- y (1.5 - x/2 y^2) on the FMA pipe (1.7e-3, 4.4e-6, then the FP32
+// rounding level: measured against MUFU.RSQ and float64 in tests/test_gpu_parity.py).  10 packed instructions for
+// two values against two MUFU.RSQ (8 cycles of the 16-lane XU pipe each): the ESP sum needs only 3.8 packed
+// instructions per two pair-evaluations besides the rsqrt, so it is bound by the XU pipe (96 % busy, FMA pipe under
+// half); giving every sixth z-node of a thread to this routine balances the two pipes (k1_lattice_kernel<ESP, 6, U, 1>).
+__device__ __forceinline__ u64 rsqrt2_fma(u64 x) {
+    float a, b;
+    upk2(x, a, b);
+    u64 y = pk2(__int_as_float(0x5f3759df - (__float_as_int(a) >> 1)),
+                __int_as_float(0x5f3759df - (__float_as_int(b) >> 1)));
+    const u64 hx = mul2(x, pk2(-0.5f, -0.5f));
+    const u64 c15 = pk2(1.5f, 1.5f);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) y = mul2(y, fma2(hx, mul2(y, y), c15));
+    return y;
+}
+
+template <int MODE, int PZ, int NF = 0>
 __device__ __forceinline__ void eval_pair_lattice(const PairA a, const PairB b, LatticeRegs<PZ>& r) {
     const u64 dx = add2(r.px, a.nx);
     const u64 dy = add2(r.py, a.ny);
@@ -241,7 +259,7 @@ __device__ __forceinline__ void eval_pair_lattice(const PairA a, const PairB b, 
             r2a = fmaxf(r2a, CPET_SOFT_EPS);
             r2b = fmaxf(r2b, CPET_SOFT_EPS);
         }
-        const u64 inv = pk2(rsqrt_approx(r2a), rsqrt_approx(r2b));
+        const u64 inv = (MODE == MODE_ESP && p < NF) ? rsqrt2_fma(r2) : pk2(rsqrt_approx(r2a), rsqrt_approx(r2b));
         if (MODE == MODE_ESP) {
             r.ax[p] = fma2(inv, b.q, r.ax[p]);
         } else {
@@ -255,7 +273,7 @@ __device__ __forceinline__ void eval_pair_lattice(const PairA a, const PairB b, 
     }
 }
 
-template <int MODE, int PZ, int UNROLL, int CHUNK>
+template <int MODE, int PZ, int UNROLL, int CHUNK, int NF = 0>
 __device__ __forceinline__ void eval_tile_lattice_chunked(const ChargePair* __restrict__ tile, int n,
                                                           LatticeRegs<PZ>& r, double (&acc)[PZ][3]) {
     for (int j0 = 0; j0 < n; j0 += CHUNK) {
@@ -264,7 +282,7 @@ __device__ __forceinline__ void eval_tile_lattice_chunked(const ChargePair* __re
         for (int j = j0; j < j1; ++j) {
             const PairA a = tile[j].a;
             const PairB b = tile[j].b;
-            eval_pair_lattice<MODE, PZ>(a, b, r);
+            eval_pair_lattice<MODE, PZ, NF>(a, b, r);
         }
 #pragma unroll
         for (int p = 0; p < PZ; ++p) {

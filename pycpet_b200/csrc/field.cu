@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) soften_scan_kernel(const ChargePair* __re
     if (hit) *flag = 1u;
 }
 
-template <int MODE, int PZ, int U>
+template <int MODE, int PZ, int U, int NF = 0>    // NF: z-nodes per thread whose rsqrt runs on the FMA pipe (ESP only)
 __global__ void __launch_bounds__(256) k1_lattice_kernel(const K1LatParams prm) {
     if (prm.soft_flag != nullptr) {
         const bool need_soft = (*prm.soft_flag != 0u);
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(256) k1_lattice_kernel(const K1LatParams prm) 
         const int stage = t % S;
         mbar_wait(&full[stage], (uint32_t)((t / S) & 1));
         const int n_t = min(TP, npairs - t * TP);
-        eval_tile_lattice_chunked<MODE, PZ, U, 64>(ring + (size_t)stage * TP, n_t, r, acc);
+        eval_tile_lattice_chunked<MODE, PZ, U, 64, NF>(ring + (size_t)stage * TP, n_t, r, acc);
         if (t + S < ntiles) {
             __syncthreads();
             if (tid == 0) issue(t + S);
@@ -398,9 +398,9 @@ __global__ void k1_lattice_finalize_kernel(const double* __restrict__ partial, i
     store_result(out_kind, step, out, i, xs[col / ny], ys[col % ny], zs[iz], s0, s1, s2);
 }
 
-template <int MODE, int PZ, int U>
+template <int MODE, int PZ, int U, int NF = 0>
 static int launch_k1_lat_inst(cpet_ctx* c, const K1LatParams& prm, dim3 grid, int threads, size_t smem) {
-    auto kern = k1_lattice_kernel<MODE, PZ, U>;
+    auto kern = k1_lattice_kernel<MODE, PZ, U, NF>;
     CPET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, c->stream>>>(prm);
     CPET_CUDA_TRY(cudaGetLastError());
@@ -423,7 +423,11 @@ int launch_field_lattice(cpet_ctx* c, int mode, int nx, int ny, int nz, const fl
     // measured (profiles/round1_lattice_sweep.txt): 5 z-nodes/thread + unroll 4 is fastest (3.05e12
     // pair-evals/s at 100^3 x 100k); take 4 nodes when that pads the z axis noticeably less
     int PZ = tu.k1_points;
-    if (PZ != 2 && PZ != 4 && PZ != 5) {
+    // ESP on large meshes: 6 z-nodes per thread, one of them with its rsqrt on the FMA pipe (the sum is bound by the
+    // 16-lane special-function unit otherwise; common.cuh: rsqrt2_fma)
+    const bool esp_mix = mode == MODE_ESP && (tu.k1_esp_mix > 0 || (tu.k1_esp_mix < 0 && n_points >= 100000 && PZ <= 0));
+    if (esp_mix) PZ = 6;
+    if (PZ != 2 && PZ != 4 && PZ != 5 && PZ != 6) {
         const double pad5 = (double)((nz + 4) / 5 * 5) / nz, pad4 = (double)((nz + 3) / 4 * 4) / nz;
         PZ = (pad5 <= pad4 * 1.02) ? 5 : 4;
         // meshes below ~1e5 nodes (17^3 ... 41^3) need the threads more than the sharing
@@ -520,7 +524,11 @@ int launch_field_lattice(cpet_ctx* c, int mode, int nx, int ny, int nz, const fl
         }
         rc = CPET_LAT_CASE(MODE_FIELD_SOFT);       // runs only when it found something (or no scan)
     } else if (mode == MODE_FIELD_RAW) rc = CPET_LAT_CASE(MODE_FIELD_RAW);
-    else rc = CPET_LAT_CASE(MODE_ESP);
+    else if (PZ == 6) {
+        rc = U == 1 ? launch_k1_lat_inst<MODE_ESP, 6, 1, 1>(c, prm, grid, threads, smem)
+                    : (U == 4 ? launch_k1_lat_inst<MODE_ESP, 6, 4, 1>(c, prm, grid, threads, smem)
+                              : launch_k1_lat_inst<MODE_ESP, 6, 2, 1>(c, prm, grid, threads, smem));
+    } else rc = CPET_LAT_CASE(MODE_ESP);
 #undef CPET_LAT_CASE
 #undef CPET_LAT_PZ
     if (rc) return rc;
