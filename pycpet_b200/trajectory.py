@@ -86,6 +86,9 @@ def topology_trajectory(engine, n_frames, frame_charges, seeds, n_iter, step_siz
     t["streamlines_s"] = t1 - t0
     plan = device_bin_plan(engine, rows, n_ref=L)
     d_range, c_range, nd, nc = plan
+    if nd < 1 or nc < 1 or nd * nc > 50_000_000:
+        raise ValueError(f"bin plan of UC:664-685 gives {nd} x {nc} bins (ranges {d_range}, {c_range}): the inter-quartile "
+                         "range of a column is degenerate for these lines")
     t2 = tick()
     t["bin_plan_s"] = t2 - t1
     de = np.linspace(d_range[0], d_range[1], nd + 1)

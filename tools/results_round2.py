@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Collect the round-2 bench.py / config4 JSON lines under gpurun_out/ into profiles/round2_results.md
+(and the raw lines into profiles/round2_lines.jsonl)."""
+import glob
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GO = os.path.join(ROOT, "gpurun_out")
+
+
+def last_json(path):
+    if not os.path.exists(path):
+        return None
+    for line in reversed(open(path).read().strip().splitlines()):
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except ValueError:
+                continue
+    return None
+
+
+md = ["# Round 2 -- measured lines (B200, one process per GPU; `tools/gpu_r2g.sh`, `tools/gpu_multi.sh`)\n",
+      "`value` = device-resident inputs, CUDA-event timed per step, L2 flushed between steps; `e2e` = the same metric with host",
+      "buffers, copies inside the timed region; kernel fraction = 20 flop (ESP: 11) x pair-evaluations of the dominant kernel's",
+      "launch / its own duration / 74.45 TFLOP/s nominal FP32 peak (148 SM x 128 lanes x 2 x 1.965 GHz).  Raw lines:",
+      "profiles/round2_lines.jsonl.\n"]
+raw = []
+d = last_json(os.path.join(GO, "round2_bench_topo3a.log"))
+ref = last_json(os.path.join(GO, "round2_bench_reference.log"))
+if d:
+    raw.append(d)
+    md += ["## One GPU: `python bench.py --steps 20 --warmup 5` (the driver's command)\n",
+           "| workload | dominant kernel | value pair-evals/s | ms/step | e2e pair-evals/s | kernel fraction of nominal FP32 peak | kernel ms |",
+           "|---|---|---|---|---|---|---|"]
+
+    def row(name, o):
+        r = o["roofline"]
+        extra = f" (MUFU bound {r['mufu_frac']:.2f})" if "mufu_frac" in r else ""
+        return (f"| `{name}` | `{r['kernel']}` | {o['value']:.4e} | {o['ms_per_step']:.3f} | {o['e2e']['value']:.4e} | "
+                f"{r['frac_nominal']:.3f}{extra} | {r['kernel_ms']:.4f} |")
+    md.append(row(d["config"]["name"], d))
+    for k, o in d.get("others", {}).items():
+        md.append(row(k, o))
+    s = d.get("sustained")
+    if s:
+        md += ["", f"Sustained: the same step loop for {s['seconds']:.1f} s ({s['steps']} steps): {s['value']:.4e} pair-evals/s "
+                   f"({s['fp32_frac_of_nominal']:.3f} of the nominal peak for the WHOLE step), SM clock median {s['sm_mhz']} MHz "
+                   f"(min {s['sm_mhz_min']}), power max {s['power_w_max']:.0f} W, throttle reasons {s['reasons'] or 'none'}."]
+    md += ["", f"Timed region: clocks {d['clocks']['sm_mhz']} MHz median, reasons {d['clocks']['reasons'] or 'none'}; "
+               f"parity_checked {d['parity_checked']} ({d['parity']}); gpu_launches {d['gpu_launches']}."]
+    cb = d.get("cpu_baseline")
+    if cb:
+        md += [f"CPU baseline in the same run: {cb['value']:.4e} pair-evals/s on {cb['cores']} cores ({cb['kind']}: {cb['impl']}; {cb['sample']})."]
+if ref:
+    raw.append(ref)
+    md += [f"Reference arm (`bench.py --impl reference --steps 20 --warmup 5`): {ref['value']:.4e} pair-evals/s on "
+           f"{ref['cpu_baseline']['cores']} host cores ({ref['cpu_baseline']['sample']}).  The C code executes K + 4 field "
+           "evaluations per line and is credited K + 2 like the GPU arm, i.e. about 20 % less than its executed work."]
+    if d:
+        md += [f"e2e / reference = {d['e2e']['value'] / ref['value']:.0f}x on this box."]
+
+md += ["", "## Weak scaling: `bench.py --gpus N` (one 3A frame per GPU per step, per-frame histograms all-gathered)\n",
+       "| N | value pair-evals/s | ms/step | e2e | parity_checked | per-rank median step ms | per-rank kernel ms |", "|---|---|---|---|---|---|---|"]
+one = d["value"] if d else None
+for n in (1, 2, 4, 8):
+    f = os.path.join(GO, "round2_bench_topo3a.log" if n == 1 else f"r2_bench_topo3a_{n}gpu.log")
+    o = last_json(f)
+    if not o:
+        continue
+    if n > 1:
+        raw.append(o)
+    eff = f" ({o['value'] / (n * one):.3f} of N x one GPU)" if one else ""
+    md.append(f"| {n} | {o['value']:.4e}{eff} | {o['ms_per_step']:.4f} | {o['e2e']['value']:.4e} | {o.get('parity_checked')} | "
+              f"{o['step_ms_by_rank']['median']} | {o['step_ms_by_rank']['kernel_mean']} |")
+
+for title, tag, note in (("Strong scaling, one 1M-line frame dealt by streamlines: `bench.py --workload md1m --split seeds`", "split_seeds",
+                          "rows all-gathered (8 MB) and restored to seed order on every rank, histogram on every rank"),
+                         ("Strong scaling, one 464^3 x 100k mesh by slabs of x-planes: `bench.py --workload volume464 --split slab`", "split_slab",
+                          "(N,6) f32 rows all-gathered (2.4 GB) on every rank inside the timed bracket")):
+    md += ["", f"## {title}\n", note + ".\n",
+           "| N | value pair-evals/s | ms/step | speed-up | e2e | parity_checked | rank kernel ms | gather ms | gather GB/s |", "|---|---|---|---|---|---|---|---|---|"]
+    base = None
+    for n in (1, 2, 4, 8):
+        cands = [os.path.join(GO, f"r2_{tag}_{n}gpu.log"), os.path.join(GO, f"r2b_{tag}_1.log") if n == 1 else ""]
+        o = None
+        for c in cands:
+            o = o or (last_json(c) if c else None)
+        if not o:
+            continue
+        raw.append(o)
+        base = base or (o["value"] / n if n == 1 else None)
+        lim = o["limiter"]
+        sp = f"{o['value'] / base:.2f}" if base else ""
+        gbs = f"{lim['gather_gb_per_s']:.0f}" if lim.get("gather_gb_per_s") else ""
+        md.append(f"| {n} | {o['value']:.4e} | {o['ms_per_step']:.3f} | {sp} | {o['e2e']['value']:.4e} | {o.get('parity_checked')} | "
+                  f"{lim['rank_kernel_ms']} | {lim['gather_ms']} | {gbs} |")
+
+for f in sorted(glob.glob(os.path.join(GO, "r2_config4_*gpu.json"))):
+    c = json.load(open(f))
+    raw.append(c)
+    md += ["", f"## {c['config']}\n",
+           f"`tools/config4.py` under torchrun: wall-clock **{c['wall_s']:.3f} s** for {c['pair_evals']:.4e} pair-evaluations = "
+           f"**{c['pair_evals_per_s']:.4e} pair-evals/s** ({c['streamlines_per_s']:.3e} streamlines/s; "
+           f"{c['fp32_frac_of_nominal_whole_job']:.3f} of {c['n_gpus']} x the nominal FP32 peak for the whole job, bin plan, histograms "
+           "and distance matrix included).",
+           f"Bin plan (device radix select over {c['frames'] * c['lines_per_frame']:.3e} values, all-reduced): {c['plan']}.",
+           f"Phases on rank 0 (s): {c['phases_s_rank0']}.", f"Per rank: {c['per_rank']}.", f"Checks: {c['checks']}."]
+open(os.path.join(ROOT, "profiles", "round2_results.md"), "w").write("\n".join(md) + "\n")
+with open(os.path.join(ROOT, "profiles", "round2_lines.jsonl"), "w") as fh:
+    for r in raw:
+        fh.write(json.dumps(r) + "\n")
+print("\n".join(md))

@@ -24,7 +24,9 @@ for M_ in (301, 20_000):                       # resident and streamed charge st
     ax = np.linspace(-0.5, 0.5, 9, dtype=np.float32)
     m.set_tuning(k1_softscan=1)                # scan + both lattice instantiations (one exits at once)
     m.field_lattice(ax, ax, ax, soften=True)
-    m.set_tuning(k1_softscan=-1)
+    m.set_tuning(k1_softscan=-1, k1_esp_mix=1)  # ESP lattice kernel, 6 z-nodes per thread, one rsqrt in six on the FMA pipe
+    m.esp_lattice(ax, ax, ax, concat_half=True)
+    m.set_tuning(k1_esp_mix=-1)
     seeds, n_iter, dims, _ = synth.seeds(6, 0.5, 0.1)
     for cfg in (dict(), dict(k2_cap=1), dict(k2_cap=2, k2_threads=128), dict(k2_cap=4, k2_tile_pairs=64, k2_stages=2),
                 dict(k2_form=1), dict(k2_form=2, k2_cap=4), dict(k2_form=3), dict(k2_form=3, k2_cap=8, k2_threads=64),

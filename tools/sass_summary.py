@@ -17,15 +17,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pycpet_b200", "libcpetb200.so")
 
 HOT = [
-    ("k2w_topo_kernel<false, 4, 4>", "K2 streamline integrator, charges resident in shared memory (3A / MD frames)"),
-    ("k2w_topo_kernel<true, 4, 4>", "K2, charge tiles streamed through the mbarrier ring (M > ~13.6k)"),
+    ("k2p_topo_kernel<false, 8>", "K2 streamline integrator, points-packed hybrid form (default for long queues: 3A / MD frames)"),
+    ("k2p_topo_kernel<true, 8>", "K2 points-packed, second-difference curvature instantiation"),
+    ("k2x_topo_kernel<false, 6, 4>", "K2 hybrid form with charge pairs packed (short queues)"),
+    ("k2w_topo_kernel<false, 4, 4>", "K2 round-1 direct form (k2_form=1, kept for A/B)"),
     ("k1_grid_kernel<1, 4, 1>", "K1 general, raw field, 4 points per thread"),
     ("k1_grid_kernel<0, 4, 1>", "K1 general, softened field (`volume` on non-mesh point lists), 4 points per thread"),
     ("k1_grid_kernel<2, 2, 1>", "K1 general, ESP, 2 points per thread (esp101 default)"),
     ("k1_grid_kernel<0, 1, 32>", "K1 general, 32 lanes per point (11^3 meshes, single points)"),
-    ("k1_lattice_kernel<0, 5, 4>", "K1 lattice, softened, 5 z-nodes per thread"),
-    ("k1_lattice_kernel<1, 5, 4>", "K1 lattice, unsoftened instantiation picked by the softening scan (`volume` 100^3)"),
-    ("k1_lattice_kernel<2, 5, 4>", "K1 lattice, ESP"),
+    ("k1_lattice_kernel<0, 5, 4, 0>", "K1 lattice, softened, 5 z-nodes per thread"),
+    ("k1_lattice_kernel<1, 5, 4, 0>", "K1 lattice, unsoftened instantiation picked by the softening scan (`volume` 100^3)"),
+    ("k1_lattice_kernel<2, 5, 4, 0>", "K1 lattice, ESP, every rsqrt on the MUFU"),
+    ("k1_lattice_kernel<2, 6, 4, 1>", "K1 lattice, ESP, 6 z-nodes per thread, one rsqrt in six on the FMA pipe (esp101 default)"),
     ("k3_hist2d_kernel<float, true>", "K3 2-D histogram, shared-memory bins"),
 ]
 PACKED = ("FFMA2", "FADD2", "FMUL2")
@@ -78,7 +81,10 @@ def hottest_loop(ins):
             continue
         body = ins[addrs.index(tgt):i + 1]
         packed = sum(1 for _, o, _ in body if o.split(".")[0] in PACKED)
-        score = (packed / len(body), packed)          # densest = the innermost unrolled charge loop
+        # the innermost unrolled charge loop: dense in packed instructions and, among the dense ones (the kernels carry
+        # 1-, 2- and 4-point variants of the same loop), the longest
+        dense = packed / len(body) >= 0.7
+        score = (dense, packed if dense else packed / len(body), packed)
         if packed and (best is None or score > best[0]):
             best = (score, body)
     return best[1] if best else []
@@ -99,7 +105,7 @@ def main():
         if cur and "REG:" in line:
             usage[cur] = line.strip()
             cur = None
-    print("# Static SASS evidence, round 1 (`tools/sass_summary.py`, no GPU needed)\n")
+    print("# Static SASS evidence, round 2 (`tools/sass_summary.py`, no GPU needed)\n")
     print("Built by `pycpet_b200/build.py`: `nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo`. Resource lines are")
     print("`cuobjdump -res-usage`; opcode counts are per trip through the hottest loop body (the backward branch whose")
     print("body has the highest share of packed-FP32 instructions: the innermost unrolled charge loop) and over the")
