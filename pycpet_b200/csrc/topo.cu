@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(CPET_K2_MAXT, 1) k2w_topo_kernel(const K2WPara
 
 __global__ void __launch_bounds__(256) k2x_extent_kernel(const float* __restrict__ seeds, int n_lines,
                                                          K2XMeta* __restrict__ meta) {
+    __shared__ unsigned s_m[8][3];
     unsigned m[3] = {0u, 0u, 0u};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += gridDim.x * blockDim.x) {
 #pragma unroll
@@ -432,7 +433,13 @@ __global__ void __launch_bounds__(256) k2x_extent_kernel(const float* __restrict
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const unsigned w = __reduce_max_sync(0xffffffffu, m[c]);
-        if ((threadIdx.x & 31) == 0 && w) atomicMax(&meta->ext[c], w);
+        if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5][c] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {                   // one atomic per block and axis (bit-wise max: |x| >= 0, NaN sorts last)
+        unsigned w = 0u;
+        for (int k = 0; k < 8; ++k) w = max(w, s_m[k][threadIdx.x]);
+        if (w) atomicMax(&meta->ext[threadIdx.x], w);
     }
 }
 

@@ -44,7 +44,7 @@ def frame2a(golden):
 
 def reset_tuning(m):
     m.set_tuning(k1_threads=0, k1_points=0, k1_lanes=0, k1_tile_pairs=0, k1_stages=0, k1_splits=0,
-                 k1_lattice=-1, k1_softscan=-1,
+                 k1_lattice=-1, k1_softscan=-1, k1_esp_mix=-1,
                  k2_threads=0, k2_tile_pairs=0, k2_stages=0, k2_sort=-1, k2_cap=0, k2_form=0, k2_amax=0)
 
 
@@ -263,6 +263,44 @@ def test_config3_esp_and_field_at_full_size(M):
     eg = M.field_grid(pts[perm], soften=True)
     assert M.last_path() == "general"
     assert relmax(eg, e[perm, 3:]) < 2e-6
+
+
+def test_esp_rsqrt_on_the_fma_pipe(M):
+    """ESP lattice kernel with one z-node in six taking its 1/sqrt from the FMA pipe (integer seed + three Newton
+    steps, common.cuh: rsqrt2_fma) against the all-MUFU kernel and the float64 oracle: same 1e-5 budget, and the
+    two kernels within 2e-6 of each other -- the spread lattice kernels with different z-nodes per thread show
+    among themselves (the routine is accurate to FP32 rounding, like MUFU.RSQ)."""
+    x, Q = synth.charges(20_000, seed=5, box=2.0)
+    ax = np.linspace(-2.0, 2.0, 49).astype(np.float32)          # 117,649 nodes: above the automatic threshold
+    pts = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+    reset_tuning(M)
+    M.set_charges(x, Q)
+    M.set_tuning(k1_esp_mix=0)
+    a = M.esp_lattice(ax, ax, ax)
+    M.set_tuning(k1_esp_mix=1)
+    b = M.esp_lattice(ax, ax, ax)
+    M.set_tuning(k1_esp_mix=-1)
+    c = M.esp_grid(pts)                                          # default heuristics through the point-list entry
+    assert M.last_path() == "lattice"
+    np.testing.assert_array_equal(b, c)
+    assert relmax(b, a) < 2e-6
+    idx = np.random.default_rng(2).choice(len(pts), 3000, replace=False)
+    want = f64.esp_grid(pts[idx], x, Q)
+    assert relmax(a[idx], want) < FIELD_TOL and relmax(b[idx], want) < FIELD_TOL
+    # charges next to nodes (r down to 1e-3 A) and far away (r ~ 1e3 A): the seed + Newton route over the range of r^2
+    xs = np.array([[-1.999, -2.0, -2.0], [900.0, -700.0, 800.0], [0.5, 0.5, 0.501]], np.float32)
+    qs = np.array([0.3, -0.7, 0.4], np.float32)
+    M.set_charges(xs, qs)
+    M.set_tuning(k1_esp_mix=1)
+    got = M.esp_lattice(ax[:7], ax[:6], ax[:12])
+    M.set_tuning(k1_esp_mix=-1)
+    p2 = np.stack(np.meshgrid(ax[:7], ax[:6], ax[:12], indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+    ref = f64.esp_grid(p2, xs, qs)
+    r = np.linalg.norm(p2[:, None, :].astype(np.float64) - xs[None].astype(np.float64), axis=2)
+    scale = 14.3996451 * (np.abs(qs)[None] / r).sum(axis=1)          # sum of |terms| per node
+    assert r.min() < 1.1e-3 and r.max() > 1e3
+    assert np.max(np.abs(got - ref) / scale) < 1e-6
+    reset_tuning(M)
 
 
 def test_sweep_corner_1e8_points(M):

@@ -97,7 +97,7 @@ for title, tag, note in (("Strong scaling, one 1M-line frame dealt by streamline
         md.append(f"| {n} | {o['value']:.4e} | {o['ms_per_step']:.3f} | {sp} | {o['e2e']['value']:.4e} | {o.get('parity_checked')} | "
                   f"{lim['rank_kernel_ms']} | {lim['gather_ms']} | {gbs} |")
 
-for f in sorted(glob.glob(os.path.join(GO, "r2_config4_*gpu.json"))):
+for f in sorted(glob.glob(os.path.join(GO, "r2_config4_[0-9]gpu.json"))):
     c = json.load(open(f))
     raw.append(c)
     md += ["", f"## {c['config']}\n",
