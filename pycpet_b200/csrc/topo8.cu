@@ -31,6 +31,7 @@ struct K2PParams {
     int stages;
     int resident;
     int cap;                // streamlines per warp (1, 2, 4 or 8)
+    int tail4, tail2;       // lines per warp of the grid left in the queue from which a warp tops up to 4 / to 2 only
     const float* seeds;
     const int32_t* n_iter;
     const int32_t* order;
@@ -216,7 +217,9 @@ __global__ void __launch_bounds__(CPET_K2P_MAXT, 1) k2p_topo_kernel(const K2PPar
     // 8 lines per warp while the queue is long; over its last stretch (4 lines per warp of the grid left) a
     // warp only tops up to 4, so the end of the queue is worked off by half-width passes on all warps
     int cap_now = prm.cap;
-    const long long tail_start = (long long)prm.n_lines - 4ll * (long long)gridDim.x * (long long)n_warps;
+    const long long grid_warps = (long long)gridDim.x * (long long)n_warps;
+    const long long tail_start = (long long)prm.n_lines - (long long)prm.tail4 * grid_warps;
+    const long long tail2_start = (long long)prm.n_lines - (long long)prm.tail2 * grid_warps;
     unsigned long long my_evals = 0ull;
     const float hf = prm.h;
     const float inv_hf = 1.0f / prm.h;
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(CPET_K2P_MAXT, 1) k2p_topo_kernel(const K2PPar
                 }
                 if (base + (unsigned)want >= (unsigned)prm.n_lines) exhausted = true;
                 if (cap_now > 4 && (long long)base + want >= tail_start) cap_now = 4;
+                if (cap_now > 2 && (long long)base + want >= tail2_start) cap_now = 2;
             }
         }
         // ---- compact the active slots' points to positions 0..na-1 ----------------------------------------
@@ -493,6 +497,8 @@ int launch_topo_points_packed(cpet_ctx* c, int n_lines, const float* d_seeds, co
     if (cap != 1 && cap != 2 && cap != 4 && cap != 8)
         cap = n_lines >= 8 * all_warps ? 8 : (n_lines >= 4 * all_warps ? 4 : (n_lines >= 3 * all_warps ? 2 : 1));
     prm.cap = cap;
+    prm.tail4 = tu.k2_tail4 >= 0 ? tu.k2_tail4 : 4;
+    prm.tail2 = tu.k2_tail2 >= 0 ? tu.k2_tail2 : 0;
     int grid = sms;
     const long long need_ctas = (n_lines + (long long)warps_per_cta * cap - 1) / ((long long)warps_per_cta * cap);
     if (need_ctas < grid) grid = (int)need_ctas;

@@ -189,3 +189,21 @@ def test_world_size_2_gloo(tmp_path):
         np.testing.assert_allclose(z["distance"], ohist.chi2_matrix(want_h), rtol=1e-13, atol=0)
         assert int(z["pairs"][0]) * (1 if r else 1) > 0
     assert int(np.load(tmp_path / "traj0.npz")["pairs"][0]) + int(np.load(tmp_path / "traj1.npz")["pairs"][0]) == pairs
+
+
+def test_trajectory_rejects_a_degenerate_bin_plan():
+    """Lines whose distances are all equal have a zero inter-quartile range: UC:669-685 would ask for an infinite
+    number of bins; the pipeline says so instead of launching a histogram with it."""
+    from pycpet_b200 import trajectory
+
+    class Flat(OracleEngine):
+        def topo_batch(self, seeds, n_iter, step_size, dimensions, second_diff=False, out=None, steps=None):
+            out[:, 0] = 0.25
+            out[:, 1] = torch.linspace(0.1, 2.0, out.shape[0])
+            if steps is not None:
+                steps.fill_(1)
+            return out
+
+    frame, tseeds, tn_iter, tdims = _trajectory_inputs()
+    with pytest.raises((ValueError, ZeroDivisionError, OverflowError)):
+        trajectory.topology_trajectory(Flat(), 2, frame, tseeds, tn_iter, 0.1, tdims)

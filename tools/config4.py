@@ -79,10 +79,10 @@ def main():
         dist.barrier()
     wall = time.perf_counter() - t0
     kt = eng.kernel_times()
-    # the library keeps the last 256 timed launches: integrator launches of this rank's frames, then the histogram
-    # and chi^2 launches
-    k2_ms = sorted(kt, reverse=True)[:min(len(mine), len(kt))] if len(mine) <= 250 else kt
-    busy = sum(k2_ms) * 1e-3 / max(tr["timings"]["streamlines_s"], 1e-9)
+    # the library keeps the last 256 timed launches, in launch order: the integrator launches of this rank's frames,
+    # then the histogram launch and the chi^2 launch
+    k2_ms = kt[:len(mine)] if len(kt) >= len(mine) + 2 else kt[:-2]
+    busy = sum(k2_ms) * 1e-3 / max(tr["timings"]["streamlines_s"], 1e-9) * (len(mine) / max(1, len(k2_ms)))
 
     # ---- checks -------------------------------------------------------------------------------------
     from oracle import f64, hist as ohist

@@ -24,6 +24,12 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   --log-file gpurun_out/round2_launches.csv python bench.py --steps 2 --warmup 3 --sustained 0 --others "" > gpurun_out/round2_bench_under_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k2p_topo_kernel' -c 1 \
   -o gpurun_out/round2_k2p python tools/prof_k2w.py 2 > gpurun_out/round2_prof.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2p_topo_kernel|k1_lattice_kernel|k1_grid_kernel' \
+  -o gpurun_out/round2_workloads python tools/prof_workloads.py > gpurun_out/round2_prof_workloads.log 2>&1
+timeout 300 python bench.py --workload md1m --split seeds --steps 10 > gpurun_out/r2_split_seeds_1gpu.log 2>gpurun_out/r2_split_seeds_1gpu.err
+timeout 400 python bench.py --workload volume464 --split slab --steps 2 > gpurun_out/r2_split_slab_1gpu.log 2>gpurun_out/r2_split_slab_1gpu.err
+timeout 300 python tools/esp_lattice_quick.py > gpurun_out/r2_esp_lattice_quick.log 2>&1
+timeout 300 python tools/k2_ab.py > gpurun_out/r2_k2_ab.log 2>&1
 {
   for t in memcheck racecheck initcheck synccheck; do
     echo "== $t"; timeout 900 compute-sanitizer --tool $t python tools/sanitize_target.py 2>&1 | grep -E "sanitize target done|ERROR SUMMARY|RACECHECK SUMMARY|hazard|Error" | head -8

@@ -2,9 +2,9 @@
 """One launch of the dominant kernel of every bench.py workload (same synthetic inputs), for
 `ncu --set full`: the per-launch DRAM traffic that bench.py reports as roofline.traffic.
 
-    ncu --set full --clock-control none -k regex:"k1_grid|k2w_topo|k1_lattice" -o gpurun_out/prof_workloads \
+    ncu --set full --clock-control none -k regex:"k1_grid|k2p_topo|k1_lattice" -o gpurun_out/round2_workloads \
         python tools/prof_workloads.py
-    python tools/prof_workloads.py --collect gpurun_out/prof_workloads.ncu-rep   # -> profiles/round1_traffic.json
+    python tools/prof_workloads.py --collect gpurun_out/round2_workloads.ncu-rep [round2]   # -> profiles/round2_traffic.json
 """
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,7 +20,7 @@ if len(sys.argv) > 2 and sys.argv[1] == "--collect":
         v = float(r[idx[k]].replace(",", "")); u = units[idx[k]].lower()
         return int(round(v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]))
     launches = [r for r in rows[2:] if "finalize" not in r[idx["Kernel Name"]] and
-                (float(r[idx["gpu__time_duration.sum"]].replace(",", "")) > 0.008 or "k2w" in r[idx["Kernel Name"]])]
+                (float(r[idx["gpu__time_duration.sum"]].replace(",", "")) > 0.008 or "_topo_kernel" in r[idx["Kernel Name"]])]
     # the softened lattice instantiation that exits at once is not a workload kernel
     launches = [r for r in launches if not ("k1_lattice" in r[idx["Kernel Name"]] and to_bytes(r, "dram__bytes_read.sum") < 40000
                                             and float(r[idx["gpu__time_duration.sum"]].replace(",", "")) < 0.01)]
@@ -32,7 +32,8 @@ if len(sys.argv) > 2 and sys.argv[1] == "--collect":
                      "duration_ms_under_ncu": float(r[idx["gpu__time_duration.sum"]].replace(",", "")) *
                      {"ms": 1.0, "msecond": 1.0, "us": 1e-3, "usecond": 1e-3, "s": 1e3, "second": 1e3, "ns": 1e-6, "nsecond": 1e-6}[units[idx["gpu__time_duration.sum"]].lower()],
                      "source": f"ncu --set full --clock-control none, one launch, {os.path.basename(sys.argv[2])} (tools/prof_workloads.py)"}
-    json.dump(out, open(os.path.join(ROOT, "profiles", "round1_traffic.json"), "w"), indent=1)
+    rnd = sys.argv[3] if len(sys.argv) > 3 else "round2"
+    json.dump(out, open(os.path.join(ROOT, "profiles", f"{rnd}_traffic.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
     sys.exit(0)
 
@@ -54,6 +55,7 @@ for name in ORDER:
         else:
             eng.field_grid(pts, soften=True, concat=True)
     else:
-        eng.esp_grid(torch.from_numpy(inp["points"]).cuda(), concat_half=True)
+        ax = torch.from_numpy(inp["axis"]).cuda()
+        eng.esp_lattice(ax, ax, ax, concat_half=True)
     torch.cuda.synchronize()
 print("done")

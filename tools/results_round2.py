@@ -21,7 +21,7 @@ def last_json(path):
     return None
 
 
-md = ["# Round 2 -- measured lines (B200, one process per GPU; `tools/gpu_r2g.sh`, `tools/gpu_multi.sh`)\n",
+md = ["# Round 2 -- measured lines (B200, one process per GPU; `tools/gpu_round2.sh`, `tools/gpu_multi.sh`)\n",
       "`value` = device-resident inputs, CUDA-event timed per step, L2 flushed between steps; `e2e` = the same metric with host",
       "buffers, copies inside the timed region; kernel fraction = 20 flop (ESP: 11) x pair-evaluations of the dominant kernel's",
       "launch / its own duration / 74.45 TFLOP/s nominal FP32 peak (148 SM x 128 lanes x 2 x 1.965 GHz).  Raw lines:",

@@ -34,6 +34,20 @@ __device__ __forceinline__ u64 rsq2(u64 t) {
 
 template <int FORM, int P>
 __device__ __forceinline__ void eval(const V16 v0, const V16 v1, const u64 v2, Regs<FORM, P>& r) {
+    if (FORM == 12) {
+        // DP12: direct form with the packing swapped: c0..2 = {p} packed over two points, charge = .F32 operands
+        float nx, ny, nz, q;
+        upk2(v0.a, nx, ny); upk2(v0.b, nz, q);
+#pragma unroll
+        for (int p = 0; p < P / 2; ++p) {
+            const u64 dx = add2(r.c0[p], pk2(nx, nx)), dy = add2(r.c1[p], pk2(ny, ny)), dz = add2(r.c2[p], pk2(nz, nz));
+            u64 r2 = mul2(dx, dx); r2 = fma2(dy, dy, r2); r2 = fma2(dz, dz, r2);
+            const u64 inv = rsq2(r2);
+            const u64 s2 = mul2(mul2(inv, inv), mul2(inv, pk2(q, q)));
+            r.a0[p] = fma2(s2, dx, r.a0[p]); r.a1[p] = fma2(s2, dy, r.a1[p]); r.a2[p] = fma2(s2, dz, r.a2[p]);
+        }
+        return;
+    }
     if (FORM == 9 || FORM == 10 || FORM == 11) {
         // XP10: P points in P/2 packed pairs; ONE charge per lane and step: v0 = {x,y,z,|x|^2}, v1 = {q,qx,qy,qz};
         // c0..2 = {-2p} packed over the two points, c3 = {|p|^2}; every charge operand is a .F32 broadcast
@@ -101,7 +115,10 @@ __global__ void __launch_bounds__(T, 1) kLoop(const UBlock* __restrict__ g, int 
 #pragma unroll
         for (int p = 0; p < P; ++p) {
             const float x = px + 0.01f * p, y = py - 0.02f * p, z = pz + 0.03f * p;
-            if (FORM == 9 || FORM == 10 || FORM == 11) {
+            if (FORM == 12) {
+                if (p < P / 2) { r.c0[p] = pk2(x, x + 0.005f); r.c1[p] = pk2(y, y + 0.007f); r.c2[p] = pk2(z, z - 0.004f); r.c3[p] = 0ull; }
+            }
+            else if (FORM == 9 || FORM == 10 || FORM == 11) {
                 if (p < P / 2) {
                     const float x1 = x + 0.005f, y1 = y + 0.007f, z1 = z - 0.004f;
                     r.c0[p] = pk2(-2 * x, -2 * x1); r.c1[p] = pk2(-2 * y, -2 * y1); r.c2[p] = pk2(-2 * z, -2 * z1);
@@ -201,6 +218,7 @@ int main(int argc, char** argv) {
         R(3, 4, 4, 384, "X10F") R(3, 4, 2, 384, "X10F") R(3, 4, 4, 512, "X10F")
         R(2, 2, 4, 512, "X10") R(2, 2, 4, 768, "X10") R(2, 3, 4, 512, "X10")
         R(0, 2, 4, 768, "D12") R(1, 2, 4, 768, "X11")
+        R(12, 8, 4, 384, "DP12") R(12, 8, 4, 256, "DP12") R(12, 8, 8, 256, "DP12") R(12, 4, 8, 256, "DP12") R(12, 4, 8, 512, "DP12") R(0, 4, 4, 256, "D12")
         R(9, 8, 4, 384, "XP10") R(9, 8, 4, 512, "XP10") R(9, 8, 8, 384, "XP10") R(9, 8, 2, 512, "XP10") R(9, 4, 8, 512, "XP10")
         R(9, 8, 6, 384, "XP10") R(10, 8, 4, 384, "XP10noMUFU") R(11, 8, 4, 384, "XP10noLDS") R(5, 4, 4, 512, "X10noLDS") R(6, 4, 4, 512, "D12noLDS")
         R(4, 4, 4, 512, "X10noMUFU") R(7, 4, 4, 512, "X10dup") R(8, 4, 4, 512, "X10dupnoMUFU") R(7, 4, 4, 384, "X10dup")
