@@ -270,14 +270,20 @@ def run_gpu(args, rank, world, local_rank, sub=False):
                 else torch.empty((n, 4), dtype=torch.float16, device=dev))
     pending = []        # in-flight NCCL gathers of per-frame histograms (world > 1)
     pool_counts = [None] * len(pool)    # this rank's own histogram of every pool frame (probe pass)
-    if kind == "topo" and world > 1:
-        # preallocated gather ring, one slot per step of a timed region (+ the gathers still in flight from
-        # the warm-up): all_gather_into_tensor writes slot i, nothing is allocated inside the timed region
-        # and every gathered histogram of the timed steps is still there for the parity check afterwards
-        n_ring = args.steps + GATHER_WINDOW + 2
-        ring = torch.empty((n_ring, world, 50, 50), dtype=torch.int64, device=dev)
-        snaps = torch.empty((n_ring, 1, 50, 50), dtype=torch.int64, device=dev)
-        ring_step = [-1] * n_ring       # global step number whose histograms slot i holds
+    # histograms gathered per NCCL call: 1 = one all-gather per frame (default); W > 1 batches W frames per call;
+    # 0 = no gathers at all (diagnostic only: how much of the N-GPU step is the exchange and its interference)
+    GW = int(getattr(args, "gather_every", 1))
+    if kind == "topo" and world > 1 and GW > 0:
+        # preallocated gather ring, one slot per batch of GW steps (enough slots for a timed region + the gathers
+        # still in flight from the warm-up): all_gather_into_tensor writes slot i, nothing is allocated inside the
+        # timed region and every gathered histogram of the timed steps is still there for the parity check afterwards
+        n_ring = (args.steps + GATHER_WINDOW * GW) // GW + 4
+        ring = torch.empty((n_ring, world, GW, 50, 50), dtype=torch.int64, device=dev)
+        snaps = torch.empty((n_ring, GW, 50, 50), dtype=torch.int64, device=dev)
+        ring_step = [[-1] * GW for _ in range(n_ring)]      # global step number whose histograms slot i, entry j holds
+
+    def issue_gather(slot):
+        pending.append(dist.all_gather_into_tensor(ring[slot].view(world * GW, 50, 50), snaps[slot], async_op=True))
 
     def drain(keep=0):
         """Wait for the oldest histogram gathers until at most `keep` are in flight."""
@@ -307,14 +313,15 @@ def run_gpu(args, rank, world, local_rank, sub=False):
             if probe:
                 pool_counts[j] = dcounts[0].clone()
             n_launch += work["k_launch"] + 1
-            if world > 1:
+            if world > 1 and GW > 0:
                 # the path's one exchange: per-frame histograms to every rank.  Issued asynchronously
                 # on NCCL's stream from a snapshot of the counts, so the next frame's kernels never
                 # wait on communication; all handles are waited for before the timed region closes.
-                i = s_now % n_ring
-                snaps[i].copy_(dcounts)
-                ring_step[i] = s_now
-                pending.append(dist.all_gather_into_tensor(ring[i], snaps[i], async_op=True))
+                slot, sub = (s_now // GW) % n_ring, s_now % GW
+                snaps[slot][sub].copy_(dcounts[0])
+                ring_step[slot][sub] = s_now
+                if sub == GW - 1:
+                    issue_gather(slot)
         elif kind == "field":
             # device arm: the mesh is described by its axes (what the host entry point derives from the
             # flat list by itself, see cpet_field_grid); the e2e arm below hands over the flat list
@@ -371,6 +378,8 @@ def run_gpu(args, rank, world, local_rank, sub=False):
             step_device()                # heavy frame on one rank does not stall the others at every step
             b.record()
         evs[-1][0].record()
+        if kind == "topo" and world > 1 and GW > 1 and seq["s"] % GW != 0:
+            issue_gather(((seq["s"] - 1) // GW) % n_ring)      # the last, partly filled batch
         drain()                          # the last frame's gather, inside its own timed bracket
         evs[-1][1].record()
         barrier()
@@ -393,13 +402,13 @@ def run_gpu(args, rank, world, local_rank, sub=False):
     # N > 1: every gathered per-frame histogram of the timed steps (steps x ranks) against THIS rank's own
     # histogram of that pool frame (probe pass): rank q computed frame (q + s) mod POOL at step s.
     parity = {"checked": True, "what": []}
-    if kind == "topo" and world > 1:
+    if kind == "topo" and world > 1 and GW > 0:
         n_cmp = 0
         for sg in range(work["s_start"], work["s_start"] + args.steps):
-            i = sg % n_ring
-            ok = ring_step[i] == sg
+            slot, sub = (sg // GW) % n_ring, sg % GW
+            ok = ring_step[slot][sub] == sg
             for q in range(world):
-                ok = ok and bool(torch.equal(ring[i][q], pool_counts[(q + sg) % len(pool)]))
+                ok = ok and bool(torch.equal(ring[slot][q][sub], pool_counts[(q + sg) % len(pool)]))
                 n_cmp += 1
             parity["checked"] = parity["checked"] and ok
         parity["what"].append(f"{n_cmp} gathered per-frame histograms of the timed steps == this rank's own "
@@ -549,7 +558,10 @@ def run_gpu(args, rank, world, local_rank, sub=False):
                    "frames": (f"{len(pool)} jittered MD frames; rank r integrates frame (r + step) mod {len(pool)}; "
                               "pair_evals_per_step_per_gpu is rank 0's mean over the timed steps"
                               if kind == "topo" else "one frame per rank"),
-                   "parallelism": f"frames sharded, 1 frame per GPU per step, x{world}"},
+                   "parallelism": f"frames sharded, 1 frame per GPU per step, x{world}" + (
+                       "" if world == 1 or kind != "topo" else
+                       (", per-frame histograms all-gathered" + (f" in batches of {GW} frames" if GW > 1 else "")
+                        if GW > 0 else ", DIAGNOSTIC: histogram gathers disabled"))},
         "units_per_s": units_all * args.steps / t_dev,
         "units": "streamlines" if kind == "topo" else "grid points",
         "fp32_frac_of_nominal": value / world * flops / 1e12 / NOMINAL_FP32_TFLOPS,
@@ -969,6 +981,8 @@ def main():
     ap.add_argument("--split", default="frames", choices=["frames", "seeds", "slab"],
                     help="frames: one frame per GPU per step (weak scaling, default); seeds: ONE topology frame dealt "
                          "over the GPUs by streamlines; slab: ONE box grid split by slabs of x-planes (strong scaling)")
+    ap.add_argument("--gather-every", type=int, default=1,
+                    help="N > 1, streamline workloads: frames per histogram all-gather (0 = no gathers, diagnostic)")
     ap.add_argument("--cpu-seconds", type=float, default=None,
                     help="CPU work per cpu_baseline sample (default 12 s; reference arm: sized from steps)")
     args = ap.parse_args()

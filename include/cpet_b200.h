@@ -184,10 +184,12 @@ int cpet_topo_hist(cpet_ctx *ctx, int n_lines, const float *seeds, const int32_t
  * when n_iter_frame_stride != 0, its own n_iter row at n_iter + f*n_iter_frame_stride (0 = one row
  * shared by all frames).  counts is (n_frames,nd,nc) int64; out_rows is (n_frames,n_lines,2) f32 or
  * NULL.  Frames alternate between two internal streams, so the host<->device copies of one frame
- * overlap the kernels of its neighbours.  Result buffers (and a per-frame n_iter table) that the caller left
- * pageable are page-locked with cudaHostRegister for the duration of the call and released before it returns
- * (tuning key "frames_pin", default 1), because a copy into pageable memory would block the enqueueing thread
- * until the frame has finished; buffers that are already pinned are used as they are.
+ * overlap the kernels of its neighbours.  Pinned (page-locked) host buffers make every copy asynchronous; with
+ * plain pageable arrays (the reference's own calling convention) a copy back blocks the enqueueing thread until
+ * its frame has finished, which costs 0-1.3 % because the next frame is already queued on the other stream
+ * (103,823-line frames 2.003 against 2.004 ms, 1M-line frames 17.53 against 17.30 ms, profiles/round2_frames_pin.txt).
+ * Tuning key "frames_pin" = 1 page-locks pageable result buffers with cudaHostRegister for the duration of the
+ * call; the registration costs more than it saves at these sizes (2.21 / 18.32 ms per frame), so it is off by default.
  * Every frame's result is identical to a cpet_topo_hist call on that frame alone. */
 int cpet_topo_hist_frames(cpet_ctx *ctx, int n_frames, const int *n_charges, const float *const *x,
                           const float *const *Q, int n_lines, const float *seeds,

@@ -678,8 +678,8 @@ int cpet_topo_hist_frames(cpet_ctx* c, int n_frames, const int* n_charges, const
         return rc;
     }
     int64_t launches = 0;
-    // result buffers the caller left pageable are page-locked for the call (both streams are drained before the
-    // destructors run), so that the copies back really are asynchronous and neighbouring frames overlap
+    // frames_pin = 1: result buffers the caller left pageable are page-locked for the call (both streams are drained
+    // before the destructors run).  Off by default: measured, the registration costs more than the blocking copies
     const bool pin = c->tune.frames_pin != 0 && n_frames > 1;
     ScopedHostPin pin_rows(out_rows, out_rows ? sizeof(float) * 2 * n * (size_t)n_frames : 0, pin && n_lines > 0);
     ScopedHostPin pin_counts(counts, cbytes * (size_t)n_frames, pin);

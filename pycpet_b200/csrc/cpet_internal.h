@@ -55,7 +55,7 @@ struct Tuning {
     int k2_unroll = 0;  // hybrid kernel: far-loop unroll of the 4-point pass (3, 4 or 6; 0 = 3)
     int k2_tail4 = -1, k2_tail2 = -1;   // points-packed kernel, end of the queue (experiments; -1 = default 4 / 0)
     int k2_amax = 0;    // hybrid kernel: largest rounding amplification a far charge may have (0 = 8)
-    int frames_pin = 1; // cpet_topo_hist_frames: page-lock pageable result buffers for the call (0 = leave them pageable)
+    int frames_pin = 0; // cpet_topo_hist_frames: 1 = page-lock pageable result buffers for the call (measured slower: off)
     int timing = 0;
 };
 

@@ -337,7 +337,17 @@ def _worker(rank, size, port, tmp):
     mine = sum(by_tag[t] for t in eng.frames_seen[-steps:])
     both = torch.tensor([float(mine)], dtype=torch.float64)
     dist.all_reduce(both)
+    # the same with the histograms gathered in batches of 3 frames (7 steps: the last batch is partly filled) and
+    # with the gathers disabled (diagnostic)
+    FakeEngine.instances.clear()
+    line3 = bench.run_gpu(_args("topo3a", steps, 3, gather_every=3), rank=rank, world=size, local_rank=0)
+    FakeEngine.instances.clear()
+    line0 = bench.run_gpu(_args("topo3a", steps, 3, gather_every=0), rank=rank, world=size, local_rank=0)
     if rank == 0:
+        assert line3["parity_checked"] is True and "14 gathered" in line3["parity"]
+        assert "batches of 3" in line3["config"]["parallelism"]
+        assert line0["parity_checked"] is True and "gathered" not in line0["parity"]
+        assert "DIAGNOSTIC" in line0["config"]["parallelism"]
         with open(os.path.join(tmp, "line.json"), "w") as fh:
             json.dump({"line": line, "pairs_all": float(both[0]), "first": eng.frames_seen[0]}, fh)
     else:

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--axis", type=int, default=100)
     ap.add_argument("--charges", type=int, default=7890)
+    ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--out", default="gpurun_out/config4.json")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -68,16 +69,26 @@ def main():
     stride = max(1, L // 4096)
     trajectory.topology_trajectory(eng, world, lambda f: (resident[mine[0]], dq), dseeds[::stride].contiguous(),
                                    dnit[::stride].contiguous(), 0.1, dims)
-    eng.kernel_times()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    tr = trajectory.topology_trajectory(eng, args.frames, lambda f: (resident[f], dq), dseeds, dnit, 0.1, dims)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    wall = time.perf_counter() - t0
+    # the trajectory runs twice over the same resident frames: the first pass pays the one-off costs of this process
+    # (cudaMalloc of the ~1 GB result buffers, NCCL's first large-message setup), the second is the steady state
+    rows_buf = torch.empty((len(mine), L, 2), dtype=torch.float32, device=dev)
+    walls, phases = [], []
+    for rep in range(args.reps):
+        eng.kernel_times()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        tr = trajectory.topology_trajectory(eng, args.frames, lambda f: (resident[f], dq), dseeds, dnit, 0.1, dims,
+                                            rows_out=rows_buf)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        walls.append(time.perf_counter() - t0)
+        phases.append(dict(tr["timings"]))
+        if rep + 1 < args.reps:
+            del tr
+    wall = walls[-1]
     kt = eng.kernel_times()
     # the library keeps the last 256 timed launches, in launch order: the integrator launches of this rank's frames,
     # then the histogram launch and the chi^2 launch
@@ -148,7 +159,7 @@ def main():
             "config": f"BASELINE configs[3]: {args.frames} MD frames x {L} seeds ({args.axis}^3), {len(Q)} charges per frame, "
                       f"box 0.5 A, step 0.1 A, frames round-robin over {world} B200",
             "n_gpus": world, "frames": args.frames, "lines_per_frame": L, "charges": int(len(Q)),
-            "wall_s": wall, "pair_evals": pairs, "pair_evals_per_s": pairs / wall,
+            "wall_s": wall, "wall_s_every_pass": walls, "phases_s_rank0_every_pass": phases, "pair_evals": pairs, "pair_evals_per_s": pairs / wall,
             "streamlines_per_s": args.frames * L / wall,
             "fp32_frac_of_nominal_whole_job": pairs / wall * 20 / 1e12 / (world * 148 * 128 * 2 * 1.965e9 / 1e12),
             "plan": {"d_range": d_range, "c_range": c_range, "nd": nd, "nc": nc},

@@ -105,6 +105,8 @@ for f in sorted(glob.glob(os.path.join(GO, "r2_config4_[0-9]gpu.json"))):
            f"**{c['pair_evals_per_s']:.4e} pair-evals/s** ({c['streamlines_per_s']:.3e} streamlines/s; "
            f"{c['fp32_frac_of_nominal_whole_job']:.3f} of {c['n_gpus']} x the nominal FP32 peak for the whole job, bin plan, histograms "
            "and distance matrix included).",
+           (f"Passes over the same resident frames (first = one-off allocations and NCCL large-message setup of the process, last = "
+            f"steady state, reported above): {[round(w, 3) for w in c['wall_s_every_pass']]} s." if "wall_s_every_pass" in c else ""),
            f"Bin plan (device radix select over {c['frames'] * c['lines_per_frame']:.3e} values, all-reduced): {c['plan']}.",
            f"Phases on rank 0 (s): {c['phases_s_rank0']}.", f"Per rank: {c['per_rank']}.", f"Checks: {c['checks']}."]
 open(os.path.join(ROOT, "profiles", "round2_results.md"), "w").write("\n".join(md) + "\n")
