@@ -70,8 +70,14 @@ int cpet_last_path(cpet_ctx *ctx);
  * "k1_lattice" (-1 auto-detect meshes in the host entry point, 0 off, 1 on),
  * "k1_softscan" (-1 auto, 0 off, 1 on: prove on the device that the softening cannot act on a mesh
  * and run the unsoftened kernel, bit-identical),
- * "k2_cap" (streamlines per warp: 1, 2, 4),"k2_threads","k2_tile_pairs","k2_stages" (a tile size or
- * stage count forces the streamed charge ring),"k2_sort" (-1 auto, 0, 1),"timing" (record kernel events).
+ * "k1_esp_mix" (-1 auto, 0 off, 1 on: ESP lattice kernel with every sixth z-node's rsqrt on the FMA pipe),
+ * "k2_form" (0 auto by queue length, 1 direct-form kernel, 2 hybrid near/far kernel with charge pairs packed,
+ * 3 hybrid kernel with point pairs packed), "k2_cap" (streamlines per warp: 1, 2, 4, and 8 in the points-packed
+ * kernel),"k2_threads","k2_tile_pairs","k2_stages" (a tile size or stage count forces the streamed charge
+ * ring),"k2_unroll" (far-loop unroll of the hybrid kernels),"k2_amax" (largest rounding amplification a charge
+ * may have to take the expanded far form; default 8),"k2_tail4","k2_tail2" (end-of-queue policy of the
+ * points-packed kernel),"k2_sort" (-1 auto, 0, 1),"frames_pin" (cpet_topo_hist_frames: page-lock pageable
+ * result buffers for the call; default 0),"timing" (record kernel events).
  * value <= 0 restores the built-in heuristic (except the three-state keys). */
 int cpet_set_tuning(cpet_ctx *ctx, const char *key, int value);
 /* Counters of the last kernel-launching call: [0]=kernels launched, [1]=pair evaluations

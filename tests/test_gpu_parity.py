@@ -567,18 +567,20 @@ def test_topo_zero_charges_and_origin_seed(M):
     seeds, n_iter, dims, _ = synth.seeds(6, 0.5, 0.1)
     seeds = np.vstack([np.zeros((1, 3), np.float32), seeds]).astype(np.float32)
     n_iter = np.concatenate([[9], n_iter])
-    reset_tuning(M)
-    try:
-        want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
-        got, steps = M.topo_batch(seeds, n_iter, x, Q, 0.1, dims, want_steps=True)
-        check_lines(got, steps, want, wsteps, 0.1, curv_tol_dir(0.1))
-        keep = Q != 0.0
-        got2 = M.topo_batch(seeds, n_iter, x[keep], Q[keep], 0.1, dims)
-        same = np.abs(got2[:, 0] - got[:, 0]) < 0.05
-        assert same.mean() > 0.99
-        np.testing.assert_allclose(got2[same], got[same], rtol=0, atol=2e-5)
-    finally:
+    want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
+    for form in (0, 2, 3):                       # default choice, charge-pair-packed, points-packed hybrid kernel
         reset_tuning(M)
+        M.set_tuning(k2_form=form)
+        try:
+            got, steps = M.topo_batch(seeds, n_iter, x, Q, 0.1, dims, want_steps=True)
+            check_lines(got, steps, want, wsteps, 0.1, curv_tol_dir(0.1))
+            keep = Q != 0.0
+            got2 = M.topo_batch(seeds, n_iter, x[keep], Q[keep], 0.1, dims)
+            same = np.abs(got2[:, 0] - got[:, 0]) < 0.05
+            assert same.mean() > 0.99
+            np.testing.assert_allclose(got2[same], got[same], rtol=0, atol=2e-5)
+        finally:
+            reset_tuning(M)
 
 
 def test_topo_streamed_charges_large_frame(M):
@@ -698,11 +700,14 @@ def test_topo_hybrid_near_field_and_outside_seeds(M):
     assert np.median(np.abs(got[ok, 0] - want[ok, 0])) <= 2e-7
     assert np.quantile(np.abs(got[ok, 0] - want[ok, 0]), 0.98) <= 2e-6
     assert np.quantile(np.abs(got[ok, 1] - want[ok, 1]), 0.98) <= 2e-5 + 2e-6 / 0.1
-    M.set_tuning(k2_form=1)
-    got1, steps1 = M.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, want_steps=True)
-    same = steps == steps1
-    assert same.mean() >= 0.99
-    assert np.quantile(np.abs(got[same] - got1[same]), 0.98) <= 5e-5
+    for form in (1, 3):                          # the direct-form kernel and the points-packed hybrid kernel
+        M.set_tuning(k2_form=form)
+        got1, steps1 = M.topo_batch(seeds, n_iter, step_size=0.1, dimensions=dims, want_steps=True)
+        same = steps == steps1
+        assert same.mean() >= 0.99
+        assert np.quantile(np.abs(got[same] - got1[same]), 0.98) <= 5e-5
+        ok1 = np.isfinite(want).all(axis=1) & (steps1 == wsteps)
+        assert np.quantile(np.abs(got1[ok1, 0] - want[ok1, 0]), 0.98) <= 2e-6
     reset_tuning(M)
 
 
@@ -715,15 +720,29 @@ def test_topo_edge_cases(M, frame2a):
     for n_it in (1, 2, 50):
         n_iter = np.full(3, n_it)
         want, wsteps = f64.topo_batch(seeds, n_iter, x, Q, 0.1, dims)
-        got, steps = M.topo_batch(seeds, n_iter, x, Q, 0.1, dims, want_steps=True)
-        np.testing.assert_array_equal(steps, wsteps)
-        assert np.max(np.abs(got - want)) < 5e-5
+        for form in (0, 3):
+            M.set_tuning(k2_form=form)
+            got, steps = M.topo_batch(seeds, n_iter, x, Q, 0.1, dims, want_steps=True)
+            np.testing.assert_array_equal(steps, wsteps)
+            assert np.max(np.abs(got - want)) < 5e-5
+        M.set_tuning(k2_form=0)
     # the per-line legacy entry point (thread_operation) gives the same numbers as the batch
     one = M.thread_operation(seeds[2], 50, x, Q, 0.1, dims)
     np.testing.assert_allclose(one, got[2], rtol=0, atol=2e-6)
     # n_iter = 0: no step taken, distance exactly 0
-    z = M.topo_batch(seeds, np.zeros(3, np.int32), x, Q, 0.1, dims)
-    assert np.all(z[:, 0] == 0.0) and np.all(np.isfinite(z[:, 1]))
+    for form in (0, 3):
+        M.set_tuning(k2_form=form)
+        z = M.topo_batch(seeds, np.zeros(3, np.int32), x, Q, 0.1, dims)
+        assert np.all(z[:, 0] == 0.0) and np.all(np.isfinite(z[:, 1]))
+        assert M.topo_batch(np.zeros((0, 3), np.float32), np.zeros(0, np.int32), x, Q, 0.1, dims).shape == (0, 2)
+    # a NaN charge poisons every line exactly as it does in the reference's sums; an empty charge set gives E = 0 -> NaN (C:501)
+    for form in (0, 3):
+        M.set_tuning(k2_form=form)
+        Qn = Q.copy(); Qn[5] = np.nan
+        assert np.all(np.isnan(M.topo_batch(seeds, np.full(3, 4), x, Qn, 0.1, dims)[:, 1]))
+        e = M.topo_batch(seeds, np.full(3, 4), np.zeros((0, 3), np.float32), np.zeros(0, np.float32), 0.1, dims)
+        assert np.all(np.isnan(e[:, 1]))
+    M.set_tuning(k2_form=0)
 
 
 @pytest.mark.parametrize("m_charges", [1, 2, 63, 64, 65, 127, 129, 1000, 13500, 13700])
