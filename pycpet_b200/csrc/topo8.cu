@@ -19,8 +19,11 @@ namespace cpet {
 #ifndef CPET_K2P_MAXT
 #define CPET_K2P_MAXT 384       // 12 warps x <= 168 registers
 #endif
+// Blocks (= charges per lane) per FP32 accumulation chain.  128 -> 256 is +1.1 % (one warp reduction per pass on the
+// 3A frame instead of two) for 8.9e-6 -> 1.3e-5 maximum curvature error against float64 on 512 sampled lines
+// (tolerance 4e-5); 512 gives nothing more (profiles/round2_k2p_tuning.txt).
 #ifndef CPET_K2P_CHUNK
-#define CPET_K2P_CHUNK 128      // blocks (= charges per lane) per FP32 accumulation chain
+#define CPET_K2P_CHUNK 256
 #endif
 #define K2P_SLOTS 8
 
@@ -523,11 +526,12 @@ int launch_topo_points_packed(cpet_ctx* c, int n_lines, const float* d_seeds, co
     KernelTimer timer(c);   // brackets the integrator kernel only (the roofline's "dominant kernel")
     const bool sd = (flags & CPET_TOPO_CURV_SECOND_DIFF) != 0u;
     int rc;
-    const int unroll = tu.k2_unroll > 0 ? tu.k2_unroll : 8;      // 3A frame: 0.721 / 0.734 / 0.745 of peak at 4 / 6 / 8 (profiles/round2_k2_forms.md)
+    const int unroll = tu.k2_unroll > 0 ? tu.k2_unroll : 6;      // 3A frame: 0.760 / 0.755 / 0.752 of peak at 6 / 8 / 12 (profiles/round2_k2p_tuning.txt)
 #define K2P_LAUNCH(UU) (sd ? launch_k2p_inst<true, UU>(c, prm, grid, threads, smem) : launch_k2p_inst<false, UU>(c, prm, grid, threads, smem))
     if (unroll <= 4) rc = K2P_LAUNCH(4);
     else if (unroll <= 6) rc = K2P_LAUNCH(6);
-    else rc = K2P_LAUNCH(8);
+    else if (unroll <= 8) rc = K2P_LAUNCH(8);
+    else rc = K2P_LAUNCH(12);
 #undef K2P_LAUNCH
     if (rc) return rc;
     launches += 1;
