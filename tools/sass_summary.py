@@ -17,8 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pycpet_b200", "libcpetb200.so")
 
 HOT = [
-    ("k2p_topo_kernel<false, 8>", "K2 streamline integrator, points-packed hybrid form (default for long queues: 3A / MD frames)"),
-    ("k2p_topo_kernel<true, 8>", "K2 points-packed, second-difference curvature instantiation"),
+    ("k2p_topo_kernel<false, 6>", "K2 streamline integrator, points-packed hybrid form (default for long queues: 3A / MD frames)"),
+    ("k2p_topo_kernel<true, 6>", "K2 points-packed, second-difference curvature instantiation"),
     ("k2x_topo_kernel<false, 6, 4>", "K2 hybrid form with charge pairs packed (short queues)"),
     ("k2w_topo_kernel<false, 4, 4>", "K2 round-1 direct form (k2_form=1, kept for A/B)"),
     ("k1_grid_kernel<1, 4, 1>", "K1 general, raw field, 4 points per thread"),
