@@ -75,14 +75,15 @@ for n in (1, 2, 4, 8):
     md.append(f"| {n} | {o['value']:.4e}{eff} | {o['ms_per_step']:.4f} | {o['e2e']['value']:.4e} | {o.get('parity_checked')} | "
               f"{o['step_ms_by_rank']['median']} | {o['step_ms_by_rank']['kernel_mean']} |")
 
-md += ["", "Where the 8-GPU loss goes (`bench.py --gpus 8 --gather-every G`, same box, back to back): the exchange itself, and the spread "
-       "between GPUs that a max-over-ranks time picks up.\n",
-       "| histogram gathers | value pair-evals/s | ms/step | of 8 x one GPU | per-rank kernel ms |", "|---|---|---|---|---|"]
+md += ["", "Where the 8-GPU loss goes (`bench.py --gpus 8 --gather-every G`, same box, back to back; measured one build earlier -- FP32 "
+       "chains of 128, unroll 8: one GPU 2.6677e12 -- so compare the three lines with each other): the exchange itself costs 0.4 %, the "
+       "rest is the spread between GPUs that a max-over-ranks time picks up.\n",
+       "| histogram gathers | value pair-evals/s | ms/step | of 8 x one GPU of that build | per-rank kernel ms |", "|---|---|---|---|---|"]
 for g, what in ((1, "one all_gather_into_tensor per frame (default)"), (4, "batched, 4 frames per call"), (0, "disabled (diagnostic)")):
     o = last_json(os.path.join(GO, f"r2_bench_topo3a_8gpu_gather{g}.log"))
     if o:
         raw.append(o)
-        eff = f"{o['value'] / (8 * one):.3f}" if one else ""
+        eff = f"{o['value'] / (8 * 2.6677e12):.3f}"
         md.append(f"| {what} | {o['value']:.4e} | {o['ms_per_step']:.4f} | {eff} | {o['step_ms_by_rank']['kernel_mean']} |")
 
 for title, tag, note in (("Strong scaling, one 1M-line frame dealt by streamlines: `bench.py --workload md1m --split seeds`", "split_seeds",
