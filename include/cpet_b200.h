@@ -71,6 +71,7 @@ int cpet_last_path(cpet_ctx *ctx);
  * "k1_softscan" (-1 auto, 0 off, 1 on: prove on the device that the softening cannot act on a mesh
  * and run the unsoftened kernel, bit-identical),
  * "k1_esp_mix" (-1 auto, 0 off, 1 on: ESP lattice kernel with every sixth z-node's rsqrt on the FMA pipe),
+ * "k1_lat_nodes" (-1 auto, 0 off, 1 on: field lattice kernel with two z-nodes per packed register),
  * "k2_form" (0 auto by queue length, 1 direct-form kernel, 2 hybrid near/far kernel with charge pairs packed,
  * 3 hybrid kernel with point pairs packed), "k2_cap" (streamlines per warp: 1, 2, 4, and 8 in the points-packed
  * kernel),"k2_threads","k2_tile_pairs","k2_stages" (a tile size or stage count forces the streamed charge

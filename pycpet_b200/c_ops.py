@@ -166,8 +166,10 @@ class Math_ops:
         return out
 
     def field_lattice(self, xs, ys, zs, x=None, Q=None, soften=True, concat=False, out=None):
-        """E on the tensor-product grid xs x ys x zs (z fastest) -> (nx*ny*nz, 3 or 6) float32;
-        bit-identical to field_grid on the expanded point list, ~25 % fewer instructions."""
+        """E on the tensor-product grid xs x ys x zs (z fastest) -> (nx*ny*nz, 3 or 6) float32; ~25 % fewer
+        instructions than field_grid on the expanded point list.  Bit-identical to it in the charge-pair form
+        (meshes below 1e5 nodes, or k1_lat_nodes=0); the node-pair form large meshes take sums a node's charges in
+        index order instead of an even and an odd chain and agrees to FP32 rounding (~1e-6)."""
         if x is not None:
             self.set_charges(x, Q)
         xs, ys, zs = f32c(xs, (-1,)), f32c(ys, (-1,)), f32c(zs, (-1,))

@@ -301,6 +301,71 @@ __device__ __forceinline__ void eval_tile_lattice_chunked(const ChargePair* __re
 }
 
 // ------------------------------------------------------------------------------------------
+// Lattice variant with two z-NODES per packed register (k1_lattice_nodes_kernel): the same arithmetic per point
+// and charge -- r^2 = dz^2 + (dy^2 + dx^2), s = (inv*inv)*(inv*q), E += s*d -- but a thread's PZ nodes are packed
+// in pairs and the charges of a pair are consumed one after the other through 32-bit broadcast operands: dx, dy and
+// dx^2+dy^2 are scalars per charge and column, and only the z accumulation still reads three 64-bit registers
+// (the streamline kernel's lesson, profiles/round2_ubench2.txt; lattice loops in tools/ubench3.cu).  A node's sum
+// runs over the charges in index order (one FP32 chain instead of an even and an odd one), so the results differ
+// from the charge-pair form in the last bits.
+// ------------------------------------------------------------------------------------------
+template <int PZ>
+struct LatticeNodeRegs {
+    float x, y;                                   // the column
+    u64 pz[PZ / 2];                               // {z_2j, z_2j+1}
+    u64 ax[PZ / 2], ay[PZ / 2], az[PZ / 2];       // FP32 partials of nodes 2j (low half) and 2j+1 (high half)
+};
+
+template <int MODE, int PZ>
+__device__ __forceinline__ void eval_pair_lattice_nodes(const PairA a, const PairB b, LatticeNodeRegs<PZ>& r) {
+    float nx[2], ny[2], nz[2], q[2];
+    upk2(a.nx, nx[0], nx[1]); upk2(a.ny, ny[0], ny[1]); upk2(b.nz, nz[0], nz[1]); upk2(b.q, q[0], q[1]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float dx = r.x + nx[h], dy = r.y + ny[h];
+        const float rxy = fmaf(dy, dy, dx * dx);
+#pragma unroll
+        for (int p = 0; p < PZ / 2; ++p) {
+            const u64 dz = add2(r.pz[p], pk2(nz[h], nz[h]));
+            const u64 r2 = fma2(dz, dz, pk2(rxy, rxy));
+            float r2a, r2b;
+            upk2(r2, r2a, r2b);
+            if (MODE == MODE_FIELD_SOFT) {
+                r2a = fmaxf(r2a, CPET_SOFT_EPS);
+                r2b = fmaxf(r2b, CPET_SOFT_EPS);
+            }
+            const u64 inv = pk2(rsqrt_approx(r2a), rsqrt_approx(r2b));
+            const u64 s = mul2(mul2(inv, inv), mul2(inv, pk2(q[h], q[h])));
+            r.ax[p] = fma2(s, pk2(dx, dx), r.ax[p]);
+            r.ay[p] = fma2(s, pk2(dy, dy), r.ay[p]);
+            r.az[p] = fma2(s, dz, r.az[p]);
+        }
+    }
+}
+
+template <int MODE, int PZ, int UNROLL, int CHUNK>
+__device__ __forceinline__ void eval_tile_lattice_nodes_chunked(const ChargePair* __restrict__ tile, int n,
+                                                                LatticeNodeRegs<PZ>& r, double (&acc)[PZ][3]) {
+    for (int j0 = 0; j0 < n; j0 += CHUNK) {
+        const int j1 = min(n, j0 + CHUNK);
+#pragma unroll UNROLL
+        for (int j = j0; j < j1; ++j) {
+            const PairA a = tile[j].a;
+            const PairB b = tile[j].b;
+            eval_pair_lattice_nodes<MODE, PZ>(a, b, r);
+        }
+#pragma unroll
+        for (int p = 0; p < PZ / 2; ++p) {
+            float lo, hi;
+            upk2(r.ax[p], lo, hi); acc[2 * p][0] += (double)lo; acc[2 * p + 1][0] += (double)hi;
+            upk2(r.ay[p], lo, hi); acc[2 * p][1] += (double)lo; acc[2 * p + 1][1] += (double)hi;
+            upk2(r.az[p], lo, hi); acc[2 * p][2] += (double)lo; acc[2 * p + 1][2] += (double)hi;
+            r.ax[p] = r.ay[p] = r.az[p] = 0ull;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Streamline kernel, round 2: hybrid pair evaluation (topo.cu, k2x_topo_kernel).
 //
 // Every point of a streamline lies inside the sampling box inflated by three steps, so a charge

@@ -6,21 +6,24 @@
 //   * the torch path: compute_topo_GPU_batch_filter + CPET/utils/gpu.py:25-399
 //     (path matrix windows, Python filter loops, torch.cat dumps).
 //
-// Design: a persistent kernel, one 512-thread CTA per SM.  A warp owns up to 4 streamlines at a
-// time; its 32 lanes split the charges of the frame and every lane evaluates all of the warp's
-// current points against each charge pair it loads (4-points-per-thread register blocking, as in
-// K1).  One *pass* = the field at the warp's current points over all M charges, a transposing warp
-// reduction of the 12 FP64 sums, then lanes 0..3 advance the state machines of the 4 lines (state
-// in shared memory: current point, seed, previous unit field direction, step counters).  A finished
-// line writes {distance, curvature} and the warp pulls the next line index from a global queue
-// ordered by n_iter descending (longest-processing-time-first).
+// This file holds what the streamline kernels share -- the LPT queue sort (k2_count / scan / scatter), the per-launch
+// classification and packing of the charges against the sampling box (k2x_extent / count / scatter), the dispatch
+// (launch_topo) -- and two of the three integrator kernels:
+//   k2w_topo_kernel  round 1, direct form (12 packed FMA-pipe instructions per two pair-evaluations), kept for A/B
+//   k2x_topo_kernel  hybrid near/far form (10), two CHARGES per packed register, 4 lines per warp: short queues
+// The default for long queues, k2p_topo_kernel (hybrid form, two POINTS per packed register, 8 lines per warp), is in
+// topo8.cu.  All three are persistent kernels, one CTA per SM: a warp owns a few streamlines at a time, its 32
+// lanes split the charges of the frame and every lane evaluates all of the warp's current points against each charge
+// it loads.  One *pass* = the field at the warp's current points over all M charges, a transposing warp reduction,
+// then the owner lanes advance the state machines of the lines (state in shared memory: current point, seed,
+// previous unit field direction, step counters).  A finished line writes {distance, curvature} and the warp pulls the
+// next line index from a global queue ordered by n_iter descending (longest-processing-time-first).
 // The field at p_k is evaluated exactly once: K+2 evaluations per line (K = steps taken), versus
 // K+4 in the reference C (the first two are recomputed there) -- the two look-ahead points at
 // the end are simply the next two steps of the same integration.
 //
-// Charges: if the packed set fits in shared memory (<= ~6.8k pairs = 13.6k charges) it is loaded
-// once per CTA by TMA bulk copies and warps then run fully independently (no CTA barriers);
-// otherwise tiles stream continuously through an S-stage TMA/mbarrier ring.
+// Charges: if the packed set fits in shared memory it is loaded once per CTA by TMA bulk copies and warps then run
+// fully independently (no CTA barriers); otherwise tiles stream continuously through an S-stage TMA/mbarrier ring.
 #include "cpet_internal.h"
 
 namespace cpet {

@@ -44,7 +44,7 @@ def frame2a(golden):
 
 def reset_tuning(m):
     m.set_tuning(k1_threads=0, k1_points=0, k1_lanes=0, k1_tile_pairs=0, k1_stages=0, k1_splits=0,
-                 k1_lattice=-1, k1_softscan=-1, k1_esp_mix=-1,
+                 k1_lattice=-1, k1_softscan=-1, k1_esp_mix=-1, k1_lat_nodes=-1,
                  k2_threads=0, k2_tile_pairs=0, k2_stages=0, k2_sort=-1, k2_cap=0, k2_form=0, k2_amax=0)
 
 
@@ -213,7 +213,7 @@ def test_field_full_size_properties(M):
     # the mesh goes to the lattice kernel, its permutation to the general one: with the charge range
     # unsplit both add the same FP64 partials in the same order, so the comparison is bit for bit
     reset_tuning(M)
-    M.set_tuning(k1_splits=1)
+    M.set_tuning(k1_splits=1, k1_lat_nodes=0)        # the charge-pair form of the lattice kernel: same sums as the general kernel
     M.set_charges(x, Q)
     e = M.field_grid(pts, soften=True)
     assert M.last_path() == "lattice"
@@ -229,6 +229,9 @@ def test_field_full_size_properties(M):
     reset_tuning(M)
     idx = rng.choice(len(pts), 2000, replace=False)
     assert relmax(e[idx], f64.field_grid(pts[idx], x, Q, True)) < FIELD_TOL
+    en = M.field_grid(pts, soften=True)               # default for a mesh of this size: node pairs packed
+    assert M.last_path() == "lattice" and relmax(en, e) < 2e-6
+    assert relmax(en[idx], f64.field_grid(pts[idx], x, Q, True)) < FIELD_TOL
     phi = M.esp_grid(pts)
     assert relmax(phi[idx], f64.esp_grid(pts[idx], x, Q)) < FIELD_TOL
 
@@ -386,6 +389,48 @@ def test_field_lattice_matches_general_kernel(M, frame2a, shape):
     assert relmax(out[:, 3:], f64.field_grid(pts, x, Q, True)) < FIELD_TOL
     assert relmax(calc.compute_field_on_grid(bumped, x, Q)[:, 3:],
                   f64.field_grid(bumped.reshape(-1, 3), x, Q, True)) < FIELD_TOL
+
+
+@pytest.mark.parametrize("shape", [(11, 11, 11), (5, 7, 23), (3, 2, 101), (6, 5, 4), (2, 3, 1), (4, 4, 16)])
+def test_field_lattice_node_pairs(M, frame2a, shape):
+    """The lattice kernel with two z-nodes per packed register (large-mesh default; forced here on small meshes) against
+    the charge-pair form, the oracle, with the charge range split, with the z axis shorter than / not a multiple of
+    the nodes per thread, softened with a charge sitting on a node, and raw."""
+    x, Q = frame2a
+    rng = np.random.default_rng(sum(shape))
+    axes = [np.sort(rng.uniform(-0.5, 0.5, n)).astype(np.float32) for n in shape]
+    pts = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+    xs = np.vstack([x, [[axes[0][0], axes[1][0], axes[2][-1]]]]).astype(np.float32)      # a charge ON the last z-node of column 0
+    qs = np.concatenate([Q, [0.25]]).astype(np.float32)
+    reset_tuning(M)
+    M.set_charges(xs, qs)
+    for soften in (True, False):
+        M.set_tuning(k1_lat_nodes=0, k1_points=0, k1_splits=0)
+        base = M.field_lattice(*axes, soften=soften)
+        want = f64.field_grid(pts, xs, qs, soften) if soften else None
+        for cfg in (dict(k1_points=8), dict(k1_points=10), dict(k1_points=6, k1_unroll=2), dict(k1_points=4, k1_splits=3),
+                    dict(k1_points=8, k1_splits=1), dict()):
+            M.set_tuning(k1_points=0, k1_splits=0, k1_unroll=0)
+            M.set_tuning(k1_lat_nodes=1, **cfg)
+            got = M.field_lattice(*axes, soften=soften)
+            if soften:
+                assert np.all(np.isfinite(got))
+                assert relmax(got, want) < FIELD_TOL, cfg
+                assert relmax(got, base) < 2e-6, cfg
+            else:                                      # the coincident node is inf / NaN exactly where the charge-pair form has it
+                fin = np.isfinite(base)
+                assert np.array_equal(np.isfinite(got), fin), cfg
+                assert np.max(np.abs(got[fin] - base[fin])) <= 2e-6 * np.max(np.abs(base[fin])), cfg
+        M.set_tuning(k1_lat_nodes=1, k1_softscan=1, k1_points=0, k1_splits=0, k1_unroll=0)   # scan + both instantiations
+        if soften:
+            assert relmax(M.field_lattice(*axes, soften=True), want) < FIELD_TOL
+        M.set_tuning(k1_softscan=-1)
+    # the point-list entry recognises the mesh and takes the same kernel
+    M.set_tuning(k1_lat_nodes=1, k1_lattice=1)
+    a = M.field_grid(pts, soften=True)
+    if M.last_path() == "lattice":
+        np.testing.assert_array_equal(a, M.field_lattice(*axes, soften=True))
+    reset_tuning(M)
 
 
 def test_field_lattice_softening_scan(M, frame2a):

@@ -24,6 +24,11 @@ for M_ in (301, 20_000):                       # resident and streamed charge st
     ax = np.linspace(-0.5, 0.5, 9, dtype=np.float32)
     m.set_tuning(k1_softscan=1)                # scan + both lattice instantiations (one exits at once)
     m.field_lattice(ax, ax, ax, soften=True)
+    m.set_tuning(k1_lat_nodes=1)               # field lattice kernel with node pairs packed (+ scan, both instantiations)
+    m.field_lattice(ax, ax, ax, soften=True)
+    m.set_tuning(k1_points=6, k1_splits=2)
+    m.field_lattice(ax, ax[:5], ax[:7], soften=False)
+    m.set_tuning(k1_points=0, k1_splits=0, k1_lat_nodes=-1)
     m.set_tuning(k1_softscan=-1, k1_esp_mix=1)  # ESP lattice kernel, 6 z-nodes per thread, one rsqrt in six on the FMA pipe
     m.esp_lattice(ax, ax, ax, concat_half=True)
     m.set_tuning(k1_esp_mix=-1)
