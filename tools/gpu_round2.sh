@@ -27,7 +27,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k2p
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2p_topo_kernel|k1_lattice_kernel|k1_grid_kernel' \
   -o gpurun_out/round2_workloads python tools/prof_workloads.py > gpurun_out/round2_prof_workloads.log 2>&1
 timeout 300 python bench.py --workload md1m --split seeds --steps 10 > gpurun_out/r2_split_seeds_1gpu.log 2>gpurun_out/r2_split_seeds_1gpu.err
-timeout 400 python bench.py --workload volume464 --split slab --steps 2 > gpurun_out/r2_split_slab_1gpu.log 2>gpurun_out/r2_split_slab_1gpu.err
+# (the slab split at N = 1 is part of tools/gpu_multi.sh-style runs: bench.py --workload volume464 --split slab --steps 2)
+timeout 300 python tools/lattice_nodes_ab.py > gpurun_out/r2_lattice_nodes.log 2>&1
 timeout 300 python tools/esp_lattice_quick.py > gpurun_out/r2_esp_lattice_quick.log 2>&1
 timeout 300 python tools/k2_ab.py > gpurun_out/r2_k2_ab.log 2>&1
 {
