@@ -583,7 +583,8 @@ def run_gpu(args, rank, world, local_rank, sub=False):
                             "kernel_mean": [round(float(v), 4) for v in per_rank[:, 2]]},
         "roofline": {"bound": "fp32-non-tensor" if kind != "esp" else "mufu (fp32 fraction quoted at 11 flop/pair)",
                      "kernel": (work.get("path", "k2p") + "_topo_kernel" if kind == "topo" else
-                                ("k1_lattice_kernel" if len(inp["points"]) >= 4096 else "k1_grid_kernel")),
+                                (("k1_lattice_nodes_kernel" if kind == "field" and len(inp["points"]) >= 100000
+                                  else "k1_lattice_kernel") if len(inp["points"]) >= 4096 else "k1_grid_kernel")),
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_source": "measured live: register-resident FMA loop (cpet_fp32_peak_probe, "
                                     f"FFMA2 {peak_ffma2:.1f} / FFMA {peak_ffma:.1f} TFLOP/s); "
@@ -847,7 +848,8 @@ def run_split(args, rank, world, local_rank):
                              "wait for the slowest rank" if kind == "topo" else
                              "gather_ms = all_gather_into_tensor of the slabs, including the wait for the slowest rank")},
         "roofline": {"bound": "fp32-non-tensor" if kind != "esp" else "mufu (fp32 fraction quoted at 11 flop/pair)",
-                     "kernel": (eng.last_path() + "_topo_kernel") if kind == "topo" else "k1_lattice_kernel",
+                     "kernel": ((eng.last_path() + "_topo_kernel") if kind == "topo" else
+                                ("k1_lattice_nodes_kernel" if kind == "field" else "k1_lattice_kernel")),
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "peak_nominal": NOMINAL_FP32_TFLOPS, "frac_nominal": achieved / NOMINAL_FP32_TFLOPS,
                      "flops_per_pair": flops, "kernel_ms": float(allr[0, 3]), "traffic": None},

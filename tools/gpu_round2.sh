@@ -24,7 +24,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   --log-file gpurun_out/round2_launches.csv python bench.py --steps 2 --warmup 3 --sustained 0 --others "" > gpurun_out/round2_bench_under_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k2p_topo_kernel' -c 1 \
   -o gpurun_out/round2_k2p python tools/prof_k2w.py 2 > gpurun_out/round2_prof.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2p_topo_kernel|k1_lattice_kernel|k1_grid_kernel' \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k2p_topo_kernel|k1_lattice|k1_grid_kernel' \
   -o gpurun_out/round2_workloads python tools/prof_workloads.py > gpurun_out/round2_prof_workloads.log 2>&1
 timeout 300 python bench.py --workload md1m --split seeds --steps 10 > gpurun_out/r2_split_seeds_1gpu.log 2>gpurun_out/r2_split_seeds_1gpu.err
 # (the slab split at N = 1 is part of tools/gpu_multi.sh-style runs: bench.py --workload volume464 --split slab --steps 2)

@@ -2,7 +2,7 @@
 """One launch of the dominant kernel of every bench.py workload (same synthetic inputs), for
 `ncu --set full`: the per-launch DRAM traffic that bench.py reports as roofline.traffic.
 
-    ncu --set full --clock-control none -k regex:"k1_grid|k2p_topo|k1_lattice" -o gpurun_out/round2_workloads \
+    ncu --set full --clock-control none -k regex:"k1_grid_kernel|k2p_topo_kernel|k1_lattice" -o gpurun_out/round2_workloads \
         python tools/prof_workloads.py
     python tools/prof_workloads.py --collect gpurun_out/round2_workloads.ncu-rep [round2]   # -> profiles/round2_traffic.json
 """

@@ -89,7 +89,8 @@ for g, what in ((1, "one all_gather_into_tensor per frame (default)"), (4, "batc
 for title, tag, note in (("Strong scaling, one 1M-line frame dealt by streamlines: `bench.py --workload md1m --split seeds`", "split_seeds",
                           "rows all-gathered (8 MB) and restored to seed order on every rank, histogram on every rank"),
                          ("Strong scaling, one 464^3 x 100k mesh by slabs of x-planes: `bench.py --workload volume464 --split slab`", "split_slab",
-                          "(N,6) f32 rows all-gathered (2.4 GB) on every rank inside the timed bracket")):
+                          "(N,6) f32 rows all-gathered (2.4 GB) on every rank inside the timed bracket; measured with the charge-pair form "
+                          "of the lattice kernel (the node-pair form shipped since is +2.9 % on this mesh at every N)")):
     md += ["", f"## {title}\n", note + ".\n",
            "| N | value pair-evals/s | ms/step | speed-up | e2e | parity_checked | rank kernel ms | gather ms | gather GB/s |", "|---|---|---|---|---|---|---|---|---|"]
     base = None
