@@ -464,11 +464,11 @@ __device__ __forceinline__ void evalx_near(const V16 v0, const V16 v1, XRegs<P>&
 // far loop reads three distinct 64-bit registers any more (4 of 10 did), which is what held the charge-pair
 // form at 73.7 % of the FP32 peak in the loop microbenchmark against 79.0 % for this one
 // (tools/ubench2.cu X10 / XP10, profiles/round2_ubench2.txt).  A warp carries 8 points (4 packed pairs).
-//   far  record (24 B): a = {alpha x, alpha y, alpha z, alpha} (LDS.128), bb = {b, b} (LDS.64), b = alpha |x|^2
+//   far  record (20 B): a = {alpha x, alpha y, alpha z, alpha} (LDS.128), b = alpha |x|^2 (LDS.32)
 //   near record       : a = {2x, 2y, 2z, 4q}
 // ------------------------------------------------------------------------------------------
-struct __align__(16) PBlock { float4 a[32]; float2 bb[32]; };
-static_assert(sizeof(PBlock) == 768, "points-packed charge block must be 768 bytes");
+struct __align__(16) PBlock { float4 a[32]; float b[32]; };
+static_assert(sizeof(PBlock) == 640, "points-packed charge block must be 640 bytes");
 
 struct PRegs {
     u64 c0[4], c1[4], c2[4], c3[4];     // {-2p.x}, {-2p.y}, {-2p.z}, {|p|^2} of the point pair (positions 2j, 2j+1)
@@ -476,8 +476,9 @@ struct PRegs {
 };
 
 template <int NP>
-__device__ __forceinline__ void evalp_far(const float4 a, const u64 bb, PRegs& r) {
+__device__ __forceinline__ void evalp_far(const float4 a, const float b, PRegs& r) {
     const u64 ax = pk2(a.x, a.x), ay = pk2(a.y, a.y), az = pk2(a.z, a.z), al = pk2(a.w, a.w);   // .F32 operands
+    const u64 bb = pk2(b, b);          // a broadcast ADDEND next to a broadcast multiplicand: FFMA2 R, R.F32x2, R.F32, R.F32
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         u64 t = fma2(r.c3[p], al, bb);

@@ -530,8 +530,8 @@ __device__ __forceinline__ void k2x_store_class(XBlock* __restrict__ out, int cl
 }
 
 // The same records in the layout of the points-packed kernel (topo8.cu): 32 charges per PBlock,
-//   far : a = {alpha x, alpha y, alpha z, alpha}   bb = {b, b}      (b = alpha |x|^2, duplicated: it is the 64-bit
-//   near: a = {2x, 2y, 2z, 4q}                     bb unused         addend of the first FFMA2 of a point pair)
+//   far : a = {alpha x, alpha y, alpha z, alpha}   b = alpha |x|^2
+//   near: a = {2x, 2y, 2z, 4q}                     b unused
 __device__ __forceinline__ void k2p_store_class(PBlock* __restrict__ out, int cls, int first_block, int slot,
                                                 float x, float y, float z, float q, bool pad) {
     PBlock& blk = out[first_block + (slot >> 5)];
@@ -539,16 +539,15 @@ __device__ __forceinline__ void k2p_store_class(PBlock* __restrict__ out, int cl
     if (cls == 0) {
         blk.a[l] = pad ? make_float4(2.0f * CPET_PAD_COORD, 2.0f * CPET_PAD_COORD, 2.0f * CPET_PAD_COORD, 0.f)
                        : make_float4(2.0f * x, 2.0f * y, 2.0f * z, 4.0f * q);
-        blk.bb[l] = make_float2(0.f, 0.f);
+        blk.b[l] = 0.f;
     } else if (pad || q == 0.f) {
         blk.a[l] = make_float4(0.f, 0.f, 0.f, 0.f);
-        blk.bb[l] = make_float2(CPET_X_PAD_B, CPET_X_PAD_B);
+        blk.b[l] = CPET_X_PAD_B;
     } else {
         const double al = (q < 0.f ? -1.0 : 1.0) / ((double)q * (double)q);   // the record carries the sign of q
         const double x2 = (double)x * x + (double)y * y + (double)z * z;
         blk.a[l] = make_float4((float)(al * x), (float)(al * y), (float)(al * z), (float)al);
-        const float b = (float)(al * x2);
-        blk.bb[l] = make_float2(b, b);
+        blk.b[l] = (float)(al * x2);
     }
 }
 

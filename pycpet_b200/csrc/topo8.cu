@@ -127,7 +127,7 @@ __device__ __forceinline__ void fold8(PRegs& r, double& v, int lane) {
     v += xadd_f64(g0, g1, 1, up1);
 }
 
-// n blocks starting at `pa` (this lane's a-record of block 0; its bb-record is 512 + 8*lane - 16*lane bytes
+// n blocks starting at `pa` (this lane's a-record of block 0; its b-record is 512 + 4*lane - 16*lane bytes
 // further, passed as pb).  FP32 chains are cut every CPET_K2P_CHUNK blocks.
 template <int NP, int U, bool NEAR>
 __device__ __forceinline__ void evalp_run(const unsigned char* __restrict__ pa, const unsigned char* __restrict__ pb,
@@ -142,7 +142,7 @@ __device__ __forceinline__ void evalp_run(const unsigned char* __restrict__ pa, 
         } else {
 #pragma unroll U
             for (int j = 0; j < m; ++j, pa += sizeof(PBlock), pb += sizeof(PBlock))
-                evalp_far<NP>(*reinterpret_cast<const float4*>(pa), *reinterpret_cast<const u64*>(pb), r);
+                evalp_far<NP>(*reinterpret_cast<const float4*>(pa), *reinterpret_cast<const float*>(pb), r);
         }
         n -= m;
         run += m;
@@ -156,7 +156,7 @@ __device__ __forceinline__ void evalp_blocks(const PBlock* __restrict__ tile, in
                                              int lane, PRegs& r, double& v, int& run) {
     const unsigned char* base = reinterpret_cast<const unsigned char*>(tile) - (size_t)gbase * sizeof(PBlock);
     const unsigned char* la = base + 16 * lane;
-    const unsigned char* lb = base + 512 + 8 * lane;
+    const unsigned char* lb = base + 512 + 4 * lane;
     int b = g0;
     if (b < nb_near && b < g1) {
         const int e = min(g1, nb_near);
