@@ -63,7 +63,11 @@ if ref:
 
 md += ["", "## Weak scaling: `bench.py --gpus N` (one 3A frame per GPU per step, per-frame histograms all-gathered)\n",
        "| N | value pair-evals/s | ms/step | e2e | parity_checked | per-rank median step ms | per-rank kernel ms |", "|---|---|---|---|---|---|---|"]
-one = d["value"] if d else None
+# the N > 1 lines were measured one build before the last kernel change (20-byte far records, +1.5 %): their efficiency is
+# quoted against the one-GPU value of THEIR build (2.7061e12, same script, same day)
+one = 2.7061e12
+md.insert(len(md) - 2, "N > 1 measured one build before the last kernel change (20-byte far records, +1.5 % at one GPU): efficiency is quoted "
+                       "against that build's one-GPU value, 2.7061e12.\n")
 for n in (1, 2, 4, 8):
     f = os.path.join(GO, "round2_bench_topo3a.log" if n == 1 else f"r2_bench_topo3a_{n}gpu.log")
     o = last_json(f)
@@ -71,7 +75,7 @@ for n in (1, 2, 4, 8):
         continue
     if n > 1:
         raw.append(o)
-    eff = f" ({o['value'] / (n * one):.3f} of N x one GPU)" if one else ""
+    eff = f" ({o['value'] / (n * one):.3f} of N x one GPU)" if n > 1 else " (final build)"
     md.append(f"| {n} | {o['value']:.4e}{eff} | {o['ms_per_step']:.4f} | {o['e2e']['value']:.4e} | {o.get('parity_checked')} | "
               f"{o['step_ms_by_rank']['median']} | {o['step_ms_by_rank']['kernel_mean']} |")
 
