@@ -19,7 +19,13 @@ One JSON line on stdout (rank 0):
                its duration measured live with CUDA events around that kernel alone
   cpu_baseline: the reference's own C (oracle/_ref, compiled from /root/reference in place) on
                this box's host cores, on a bounded sample of the same workload
+  sustained  : (N = 1) the same step loop continued for >= 5 s: pair-evals/s, SM clock, power, throttle reasons
+  others     : (N = 1, default workload) short records of the other BASELINE configurations (md1m, volume, esp101, volume2a)
+  parity_checked: every gathered histogram of the timed steps (N > 1) and the end-to-end call's histograms against
+               the device arm's, compared outside the timed region
 `--impl reference` times that CPU reference alone (rank 0 only) and prints the same line shape.
+`--split seeds|slab` (with --gpus N) are the strong-scaling modes: ONE 1M-line frame dealt by streamlines, ONE 464^3 mesh
+by slabs of x-planes, the final NCCL gather inside the timed bracket ("scaling": "strong").
 """
 from __future__ import annotations
 
