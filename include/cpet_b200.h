@@ -60,8 +60,8 @@ int cpet_create_on_stream(int device, void *cuda_stream, cpet_ctx **out);
 int cpet_destroy(cpet_ctx *ctx);
 int cpet_sync(cpet_ctx *ctx);
 int cpet_device_of(cpet_ctx *ctx);
-/* Diagnostic: which kernel served the last call on this context.  Field / ESP: 0 general point-list kernel,
- * 1 lattice kernel.  Streamlines: 11 direct-form kernel (k2w), 12 hybrid, charge pairs packed (k2x),
+/* Diagnostic: which kernel served the last call on this context.  Field / ESP: 0 general point-list kernel
+ * (direct form), 1 lattice kernel, 3 general point-list kernel in the hybrid near/far form.  Streamlines: 11 direct-form kernel (k2w), 12 hybrid, charge pairs packed (k2x),
  * 13 hybrid, points packed (k2p). */
 int cpet_last_path(cpet_ctx *ctx);
 /* Tuning knobs for experiments (the defaults are measured heuristics, profiles/round1_sweep.md):
@@ -72,6 +72,7 @@ int cpet_last_path(cpet_ctx *ctx);
  * and run the unsoftened kernel, bit-identical),
  * "k1_esp_mix" (-1 auto, 0 off, 1 on: ESP lattice kernel with every sixth z-node's rsqrt on the FMA pipe),
  * "k1_lat_nodes" (-1 auto, 0 off, 1 on: field lattice kernel with two z-nodes per packed register),
+ * "k1_hybrid" (-1 auto, 0 off, 1 on: field sums over >= 2,048 listed points in the hybrid near/far form),
  * "k2_form" (0 auto by queue length, 1 direct-form kernel, 2 hybrid near/far kernel with charge pairs packed,
  * 3 hybrid kernel with point pairs packed), "k2_cap" (streamlines per warp: 1, 2, 4, and 8 in the points-packed
  * kernel),"k2_threads","k2_tile_pairs","k2_stages" (a tile size or stage count forces the streamed charge

@@ -89,7 +89,7 @@ SIGNATURES = {
     "cpet_kernel_times": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), c_int, ctypes.POINTER(c_int)]),
 }
 
-PATH_NAMES = {0: "general", 1: "lattice", 11: "k2w", 12: "k2x", 13: "k2p"}     # cpet_last_path codes
+PATH_NAMES = {0: "general", 1: "lattice", 3: "general_hybrid", 11: "k2w", 12: "k2x", 13: "k2p"}     # cpet_last_path codes
 
 # the reference's own symbol names (include/cpet_b200.h section (A)); argtypes are set by Math_ops
 LEGACY_SYMBOLS = [

@@ -227,12 +227,12 @@ int cpet_set_tuning(cpet_ctx* c, const char* key, int value) {
         {"k2_threads", &t.k2_threads}, {"k2_tile_pairs", &t.k2_tile_pairs},
         {"k2_stages", &t.k2_stages}, {"k2_sort", &t.k2_sort}, {"k2_cap", &t.k2_cap},
         {"k2_form", &t.k2_form}, {"k2_amax", &t.k2_amax}, {"k2_unroll", &t.k2_unroll},
-        {"frames_pin", &t.frames_pin}, {"k1_esp_mix", &t.k1_esp_mix}, {"k1_lat_nodes", &t.k1_lat_nodes}, {"k2_tail4", &t.k2_tail4}, {"k2_tail2", &t.k2_tail2},
+        {"frames_pin", &t.frames_pin}, {"k1_esp_mix", &t.k1_esp_mix}, {"k1_lat_nodes", &t.k1_lat_nodes}, {"k1_hybrid", &t.k1_hybrid}, {"k2_tail4", &t.k2_tail4}, {"k2_tail2", &t.k2_tail2},
         {"timing", &t.timing},
     };
     for (auto& e : tab) {
         if (strcmp(e.k, key) == 0) {
-            if (e.v == &t.k2_sort || e.v == &t.k1_lattice || e.v == &t.k1_softscan || e.v == &t.k1_esp_mix || e.v == &t.k1_lat_nodes || e.v == &t.k2_tail4 || e.v == &t.k2_tail2) *e.v = value;
+            if (e.v == &t.k2_sort || e.v == &t.k1_lattice || e.v == &t.k1_softscan || e.v == &t.k1_esp_mix || e.v == &t.k1_lat_nodes || e.v == &t.k1_hybrid || e.v == &t.k2_tail4 || e.v == &t.k2_tail2) *e.v = value;
             else *e.v = value > 0 ? value : 0;
             return CPET_OK;
         }

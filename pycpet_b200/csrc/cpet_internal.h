@@ -45,6 +45,7 @@ struct Tuning {
     int k1_splits = 0;
     int k1_unroll = 0;     // lattice kernel inner-loop unroll (1, 2 or 4; 0 = default 2)
     int k1_lattice = -1;   // -1 auto (detect z-fastest tensor-product meshes in the host entry point), 0 off, 1 on
+    int k1_hybrid = -1;    // general field kernel in the hybrid near/far form: -1 auto (lists >= 2,048 points), 0 off, 1 on
     int k1_lat_nodes = -1; // field lattice kernel with node pairs packed: -1 auto (meshes >= 1e5 nodes), 0 off, 1 on
     int k1_esp_mix = -1;   // ESP lattice kernel: -1 auto (large meshes), 0 off, 1 on: every sixth z-node's rsqrt on the FMA pipe
     int k1_softscan = -1;  // lattice kernel: -1 auto (scan for charges on grid nodes when the mesh is large), 0 off, 1 on

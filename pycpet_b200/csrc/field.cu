@@ -765,6 +765,246 @@ int detect_lattice(cpet_ctx* c, int n_points, const float* d_x0, int* is_lattice
     return CPET_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1, hybrid near/far form for point LISTS (default from 2,048 points, tuning key "k1_hybrid"): the streamline kernel's
+// arithmetic (common.cuh: evalp_far / evalp_near, 10 packed FMA-pipe instructions per two pair-evaluations for
+// charges far from the points) applied to the general field sum.  The charges are classified per call against the
+// origin-centred bounding box of the point list (topo.cu: pack_hybrid; PyCPET's box frame is centred at the
+// origin -- a point cloud elsewhere simply classifies every charge as near and runs the direct form) and packed
+// as PBlocks [near | far].  A thread owns 4 points (2 packed pairs); every charge record is a broadcast LDS.128 +
+// LDS.32.  FP32 partials per point are folded into FP64 every 64 charges; E = k (p S - T) in FP64 at the end.
+// The charge (block) range can be split over gridDim.y exactly like the general kernel (FP64 partials + finalize).
+// ---------------------------------------------------------------------------------------------
+struct K1XParams {
+    const PBlock* blocks;
+    const K2XMeta* meta;
+    int tile_blocks;
+    int stages;
+    const float* x0;
+    int n_points;
+    int out_kind;
+    float step;
+    void* out;
+    double* partial;
+};
+
+template <bool SOFT>
+__device__ __forceinline__ void evalp_near2(const float4 a, PRegs& r) {
+    const u64 x2 = pk2(a.x, a.x), y2 = pk2(a.y, a.y), z2 = pk2(a.z, a.z), q4 = pk2(a.w, a.w);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const u64 dx = add2(r.c0[p], x2);          // -2 (p - x), exact
+        const u64 dy = add2(r.c1[p], y2);
+        const u64 dz = add2(r.c2[p], z2);
+        u64 r2 = mul2(dx, dx);
+        r2 = fma2(dy, dy, r2);
+        r2 = fma2(dz, dz, r2);
+        if (SOFT) {                                // max(r^2, 1e-6) (C:433-436) on |D|^2 = 4 r^2: an exact scaling
+            float lo, hi;
+            upk2(r2, lo, hi);
+            r2 = pk2(fmaxf(lo, 4.0f * CPET_SOFT_EPS), fmaxf(hi, 4.0f * CPET_SOFT_EPS));
+        }
+        const u64 inv = rsqrt2(r2);
+        const u64 s = mul2(mul2(inv, inv), mul2(inv, q4));
+        r.a0[p] = fma2(s, dx, r.a0[p]);
+        r.a1[p] = fma2(s, dy, r.a1[p]);
+        r.a2[p] = fma2(s, dz, r.a2[p]);
+    }
+}
+
+template <bool SOFT>
+__global__ void __launch_bounds__(256) k1x_grid_kernel(const K1XParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    PBlock* ring = reinterpret_cast<PBlock*>(smem_raw + 128);
+    const int tid = threadIdx.x;
+    const int S = prm.stages;
+    const int TB = prm.tile_blocks;
+    const int nb_total = prm.meta->nb_total;
+    const int nb_near = prm.meta->nb_near;
+    const int bps = (nb_total + (int)gridDim.y - 1) / (int)gridDim.y;      // blocks per split
+    const int bbeg = min(nb_total, (int)blockIdx.y * bps);
+    const int bend = min(nb_total, bbeg + bps);
+    const int nblk = bend - bbeg;
+    const int ntiles = (nblk + TB - 1) / TB;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const int stage = t % S;
+        const int n_t = min(TB, nblk - t * TB);
+        const uint32_t bytes = (uint32_t)n_t * (uint32_t)sizeof(PBlock);
+        mbar_expect_tx(&full[stage], bytes);
+        tma_load_1d(ring + (size_t)stage * TB, prm.blocks + bbeg + (size_t)t * TB, bytes, &full[stage]);
+    };
+    if (tid == 0) {
+        const int pre = min(S, ntiles);
+        for (int t = 0; t < pre; ++t) issue(t);
+    }
+
+    // this thread's 4 points = 2 packed pairs (positions 0,1 and 2,3)
+    float px[4], py[4], pz[4];
+    int pt[4];
+    const int base = blockIdx.x * 1024;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        pt[p] = base + p * 256 + tid;
+        const int ld = min(pt[p], prm.n_points - 1);
+        px[p] = prm.x0[3 * (size_t)ld + 0];
+        py[p] = prm.x0[3 * (size_t)ld + 1];
+        pz[p] = prm.x0[3 * (size_t)ld + 2];
+    }
+    PRegs r;
+    double acc[4][4];                  // per point: T.x - E_near.x, T.y - .., T.z - .., S
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        r.c0[j] = pk2(-2.0f * px[2 * j], -2.0f * px[2 * j + 1]);
+        r.c1[j] = pk2(-2.0f * py[2 * j], -2.0f * py[2 * j + 1]);
+        r.c2[j] = pk2(-2.0f * pz[2 * j], -2.0f * pz[2 * j + 1]);
+        r.c3[j] = pk2(fmaf(pz[2 * j], pz[2 * j], fmaf(py[2 * j], py[2 * j], px[2 * j] * px[2 * j])),
+                      fmaf(pz[2 * j + 1], pz[2 * j + 1], fmaf(py[2 * j + 1], py[2 * j + 1], px[2 * j + 1] * px[2 * j + 1])));
+        r.a0[j] = r.a1[j] = r.a2[j] = r.a3[j] = 0ull;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.0;
+
+    auto flush = [&]() {               // FP32 partials of the last <= 64 charges -> FP64
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float lo, hi;
+            upk2(r.a0[j], lo, hi); acc[2 * j][0] += (double)lo; acc[2 * j + 1][0] += (double)hi;
+            upk2(r.a1[j], lo, hi); acc[2 * j][1] += (double)lo; acc[2 * j + 1][1] += (double)hi;
+            upk2(r.a2[j], lo, hi); acc[2 * j][2] += (double)lo; acc[2 * j + 1][2] += (double)hi;
+            upk2(r.a3[j], lo, hi); acc[2 * j][3] += (double)lo; acc[2 * j + 1][3] += (double)hi;
+            r.a0[j] = r.a1[j] = r.a2[j] = r.a3[j] = 0ull;
+        }
+    };
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int stage = t % S;
+        mbar_wait(&full[stage], (uint32_t)((t / S) & 1));
+        const int n_t = min(TB, nblk - t * TB);
+        const PBlock* tile = ring + (size_t)stage * TB;
+        for (int b = 0; b < n_t; ++b) {
+            const int g = bbeg + t * TB + b;               // global block index: near blocks come first
+            const PBlock& blk = tile[b];
+            if (g < nb_near) {
+#pragma unroll 2
+                for (int e = 0; e < 32; ++e) evalp_near2<SOFT>(blk.a[e], r);
+            } else {
+#pragma unroll 8
+                for (int e = 0; e < 32; ++e) evalp_far<2>(blk.a[e], blk.b[e], r);
+            }
+            if (b & 1) flush();                            // chains of at most 64 charges
+        }
+        flush();
+        if (t + S < ntiles) {
+            __syncthreads();           // every warp is done reading this stage
+            if (tid == 0) issue(t + S);
+        }
+    }
+
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (pt[p] >= prm.n_points) continue;
+        // E = p*S - (T - E_near), up to the Coulomb constant (store_result applies it)
+        const double ex = (double)px[p] * acc[p][3] - acc[p][0];
+        const double ey = (double)py[p] * acc[p][3] - acc[p][1];
+        const double ez = (double)pz[p] * acc[p][3] - acc[p][2];
+        if (gridDim.y == 1) {
+            store_result(prm.out_kind, prm.step, prm.out, pt[p], px[p], py[p], pz[p], ex, ey, ez);
+        } else {
+            double* o = prm.partial + ((size_t)blockIdx.y * prm.n_points + pt[p]) * 3;
+            o[0] = ex; o[1] = ey; o[2] = ez;
+        }
+    }
+}
+
+static int launch_field_grid_hybrid(cpet_ctx* c, int mode, int n_points, const float* d_x0, int out_kind,
+                                    void* d_out, float step) {
+    const Tuning& tu = c->tune;
+    const int sms = c->sm_count;
+    int launches = 0;
+    unsigned int* queue = nullptr;
+    unsigned long long* evals = nullptr;
+    const int32_t* order = nullptr;
+    if (int rc = prepare_queue(c, n_points, nullptr, false, &queue, &evals, &order, &launches)) return rc;   // zeroes the meta block
+    const int max_blocks = (c->n_charges + 31) / 32 + 2;
+    K2XMeta* meta = nullptr;
+    const float zero3[3] = {0.f, 0.f, 0.f};
+    if (int rc = pack_hybrid(c, n_points, d_x0, 0.0f, zero3, 1, max_blocks, &meta, &launches)) return rc;
+
+    const int gx = (n_points + 1023) / 1024;
+    int splits = tu.k1_splits;
+    if (splits <= 0) {
+        // ~2 CTAs are resident per SM.  Fewer CTAs than slots: split the block range so that ONE round is as full
+        // as it gets (100,000 points: 98 CTAs x 3 splits = 294 of 296 slots, 0.72 of the peak against 0.65 with 4
+        // splits, which need a second round); more: make the last round nearly full, as the direct kernel does.
+        splits = 1;
+        const int slots = 2 * sms;
+        if (gx < slots) {
+            const int smax = max_blocks / 4 > 0 ? max_blocks / 4 : 1;          // >= 128 charges per split
+            splits = slots / gx;
+            if (splits > smax) splits = smax;
+        } else {
+            const int smax = max_blocks / 64 > 16 ? 16 : max_blocks / 64;
+            double best = 1e30;
+            for (int s = 1; s <= (smax < 1 ? 1 : smax); ++s) {
+                const double w = (double)gx * s / slots;
+                const double ineff = ceil(w) / w;
+                if (ineff < best - 0.004) { best = ineff; splits = s; }
+                if (ineff <= 1.02) break;
+            }
+        }
+    }
+    while (splits > 1 && (size_t)splits * (size_t)n_points * 24u > ((size_t)1 << 30)) --splits;
+    if (splits > max_blocks / 2) splits = max_blocks / 2 > 0 ? max_blocks / 2 : 1;
+    if (splits > 65535) splits = 65535;
+
+    K1XParams prm;
+    prm.blocks = c->xblocks.as<PBlock>();
+    prm.meta = meta;
+    prm.tile_blocks = tu.k1_tile_pairs > 0 ? (tu.k1_tile_pairs / 16 > 0 ? tu.k1_tile_pairs / 16 : 1) : 48;   // 30 KB
+    prm.stages = tu.k1_stages > 0 ? (tu.k1_stages > 8 ? 8 : tu.k1_stages) : 3;
+    prm.x0 = d_x0;
+    prm.n_points = n_points;
+    prm.out_kind = out_kind;
+    prm.step = step;
+    prm.out = d_out;
+    prm.partial = nullptr;
+    if (splits > 1) {
+        if (int rc = c->work0.reserve(sizeof(double) * 3 * (size_t)splits * (size_t)n_points)) return rc;
+        prm.partial = c->work0.as<double>();
+    }
+    const size_t smem = 128 + (size_t)prm.stages * prm.tile_blocks * sizeof(PBlock);
+    KernelTimer timer(c);
+    dim3 grid((unsigned)gx, (unsigned)splits, 1);
+    if (mode == MODE_FIELD_SOFT) {
+        auto kern = k1x_grid_kernel<true>;
+        CPET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 256, smem, c->stream>>>(prm);
+    } else {
+        auto kern = k1x_grid_kernel<false>;
+        CPET_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 256, smem, c->stream>>>(prm);
+    }
+    CPET_CUDA_TRY(cudaGetLastError());
+    launches += 1;
+    if (splits > 1) {
+        k1_finalize_kernel<<<(n_points + 255) / 256, 256, 0, c->stream>>>(prm.partial, splits, n_points, 3, d_x0,
+                                                                          out_kind, step, d_out);
+        CPET_CUDA_TRY(cudaGetLastError());
+        launches += 1;
+    }
+    c->last_counters[0] = launches;
+    c->last_path = 3;
+    return CPET_OK;
+}
+
 int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, int out_kind,
                       void* d_out, float step) {
     CPET_REQUIRE(c->charges_set, CPET_ERR_STATE, "no charge set on this context: call cpet_set_charges first");
@@ -774,6 +1014,12 @@ int launch_field_grid(cpet_ctx* c, int mode, int n_points, const float* d_x0, in
     if (n_points == 0) return CPET_OK;
     const Tuning& tu = c->tune;
     const int sms = c->sm_count;
+    // Field sums over point lists of >= 2,048 points take the hybrid near/far kernel (1e6 random points x 100,000
+    // charges: 0.78 of the FP32 peak against 0.64 softened / 0.68 raw for the direct form below; 5,000 points x 30,000
+    // charges 0.53 against 0.30; tools/k1_hybrid_ab.py, profiles/round2_k1_hybrid.txt); ESP and short lists stay here.
+    if ((tu.k1_hybrid > 0 || (tu.k1_hybrid < 0 && c->n_charges >= 256)) && mode != MODE_ESP && n_points >= 2048 &&
+        c->n_charges > 0)
+        return launch_field_grid_hybrid(c, mode, n_points, d_x0, out_kind, d_out, step);
 
     int threads = tu.k1_threads > 0 ? tu.k1_threads : 256;
     if (threads > 256) threads = 256;

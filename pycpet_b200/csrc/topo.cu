@@ -468,7 +468,8 @@ __device__ __forceinline__ int k2x_class(float x, float y, float z, float q, con
     const float ex = fmaxf(fabsf(x) - b.bx, 0.f), ey = fmaxf(fabsf(y) - b.by, 0.f), ez = fmaxf(fabsf(z) - b.bz, 0.f);
     const float r2min = ex * ex + ey * ey + ez * ez;
     const float xn = sqrtf(x * x + y * y + z * z) + b.pmax;
-    const bool far = (xn * xn <= b.amax * r2min) && (xn < 1.0e6f);      // false for NaN
+    // (r2min >= 1e-5: a far charge can never come within the 1e-3 A where the volume path's softening acts)
+    const bool far = (xn * xn <= b.amax * r2min) && (xn < 1.0e6f) && (r2min >= 1.0e-5f);      // false for NaN
     if (!far) return 0;
     if (q == 0.f) return 1;                                            // zero-weight far record
     if (!(fabsf(q) >= CPET_X_MIN_ABS_Q)) return 0;                     // tiny or NaN charge

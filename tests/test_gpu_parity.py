@@ -44,7 +44,7 @@ def frame2a(golden):
 
 def reset_tuning(m):
     m.set_tuning(k1_threads=0, k1_points=0, k1_lanes=0, k1_tile_pairs=0, k1_stages=0, k1_splits=0,
-                 k1_lattice=-1, k1_softscan=-1, k1_esp_mix=-1, k1_lat_nodes=-1,
+                 k1_lattice=-1, k1_softscan=-1, k1_esp_mix=-1, k1_lat_nodes=-1, k1_hybrid=-1,
                  k2_threads=0, k2_tile_pairs=0, k2_stages=0, k2_sort=-1, k2_cap=0, k2_form=0, k2_amax=0)
 
 
@@ -213,7 +213,7 @@ def test_field_full_size_properties(M):
     # the mesh goes to the lattice kernel, its permutation to the general one: with the charge range
     # unsplit both add the same FP64 partials in the same order, so the comparison is bit for bit
     reset_tuning(M)
-    M.set_tuning(k1_splits=1, k1_lat_nodes=0)        # the charge-pair form of the lattice kernel: same sums as the general kernel
+    M.set_tuning(k1_splits=1, k1_lat_nodes=0, k1_hybrid=0)   # charge-pair lattice form and direct-form general kernel: the same sums
     M.set_charges(x, Q)
     e = M.field_grid(pts, soften=True)
     assert M.last_path() == "lattice"
@@ -231,6 +231,8 @@ def test_field_full_size_properties(M):
     assert relmax(e[idx], f64.field_grid(pts[idx], x, Q, True)) < FIELD_TOL
     en = M.field_grid(pts, soften=True)               # default for a mesh of this size: node pairs packed
     assert M.last_path() == "lattice" and relmax(en, e) < 2e-6
+    eh = M.field_grid(pts[perm], soften=True)         # default for a point list of this size: hybrid near/far kernel
+    assert M.last_path() == "general_hybrid" and relmax(eh, e[perm]) < 2e-6
     assert relmax(en[idx], f64.field_grid(pts[idx], x, Q, True)) < FIELD_TOL
     phi = M.esp_grid(pts)
     assert relmax(phi[idx], f64.esp_grid(pts[idx], x, Q)) < FIELD_TOL
@@ -264,8 +266,63 @@ def test_config3_esp_and_field_at_full_size(M):
     # the same points in another order take the general kernel: same values within the field budget
     perm = np.random.default_rng(8).permutation(len(pts))[:200_000]
     eg = M.field_grid(pts[perm], soften=True)
-    assert M.last_path() == "general"
+    assert M.last_path() == "general_hybrid"          # a point list of this size: hybrid near/far kernel
     assert relmax(eg, e[perm, 3:]) < 2e-6
+
+
+@pytest.mark.parametrize("case", ["box", "off_centre", "charges_inside", "tiny_q_nan", "few_charges"])
+def test_field_general_hybrid_kernel(M, case):
+    """The general field kernel in its hybrid near/far form (default for lists of >= 2,048 points) against the float64
+    oracle and the direct-form kernel: points in the origin-centred box PyCPET uses, a point cloud far from the origin
+    (every charge classifies as near: plain direct form), charges INSIDE the cloud and 2e-4 A from a point (softening
+    acts, raw gives the reference's inf/NaN), zero / denormal-small / NaN charges, fewer charges than one block;
+    with the block range split, as (N,6) rows, and through propagate."""
+    rng = np.random.default_rng({"box": 1, "off_centre": 2, "charges_inside": 3, "tiny_q_nan": 4, "few_charges": 5}[case])
+    n = 5000
+    x, Q = synth.charges(3000 if case != "few_charges" else 20, seed=21, box=0.6)
+    pts = (rng.uniform(-0.6, 0.6, (n, 3))).astype(np.float32)
+    if case == "off_centre":
+        pts = (pts + np.array([40.0, -25.0, 10.0], np.float32)).astype(np.float32)
+    if case == "charges_inside":
+        x = np.vstack([x, pts[7] + np.float32(2e-4), [[0.1, 0.2, -0.3]], pts[11]]).astype(np.float32)
+        Q = np.concatenate([Q, [0.3, -0.2, 0.4]]).astype(np.float32)
+    if case == "tiny_q_nan":
+        Q = Q.copy(); Q[::5] = 0.0; Q[1::7] = np.float32(1e-25); Q[2::9] = np.float32(-3e-14)
+    reset_tuning(M)
+    M.set_charges(x, Q)
+    for soften in (True, False):
+        want = f64.field_grid(pts, x, Q, soften)
+        fin = np.isfinite(want).all(axis=1)
+        scale = np.abs(want[fin]).max()
+        M.set_tuning(k1_hybrid=0)
+        direct = M.field_grid(pts, soften=soften)
+        for cfg in (dict(k1_hybrid=-1), dict(k1_hybrid=1, k1_splits=1), dict(k1_hybrid=1, k1_splits=7),
+                    dict(k1_hybrid=1, k1_tile_pairs=64, k1_stages=2)):
+            M.set_tuning(k1_splits=0, k1_tile_pairs=0, k1_stages=0)
+            M.set_tuning(**cfg)
+            got = M.field_grid(pts, soften=soften, concat=True)
+            auto_small = cfg.get("k1_hybrid") == -1 and len(Q) < 256      # too few charges to pay for the packing
+            assert M.last_path() == ("general" if auto_small else "general_hybrid")
+            np.testing.assert_array_equal(got[:, :3], pts)
+            assert np.array_equal(np.isfinite(got[:, 3:]).all(axis=1), fin), (case, soften, cfg)
+            assert np.max(np.abs(got[fin, 3:] - want[fin])) / scale < FIELD_TOL, (case, soften, cfg)
+            # two FP32 summation orders of the same terms (one chain per point here, an even and an odd one there); a
+            # point cloud 48 A from the origin sees only far, strongly cancelling charges: 2.6e-6 between the two
+            assert np.max(np.abs(got[fin, 3:] - direct[fin])) / scale < (6e-6 if case == "off_centre" else 2e-6), (case, soften, cfg)
+        M.set_tuning(k1_splits=0, k1_tile_pairs=0, k1_stages=0, k1_hybrid=-1)
+    if case == "tiny_q_nan":                          # a NaN charge poisons every point, as in the reference's sum
+        Qn = Q.copy(); Qn[3] = np.nan
+        M.set_charges(x, Qn)
+        assert np.all(np.isnan(M.field_grid(pts, soften=True)))
+        M.set_charges(x, Q)
+    # one normalised-field step (propagate_topo) goes through the same kernel
+    step = M.propagate(pts, 0.1)
+    e = f64.field_grid(pts, x, Q, False)
+    efin = np.isfinite(e).all(axis=1)
+    ok = efin & (np.linalg.norm(np.where(efin[:, None], e, 0.0), axis=1) > 1e-6 * np.abs(e[efin]).max())
+    ref = pts.astype(np.float64) + 0.1 * e / np.linalg.norm(e, axis=1, keepdims=True)
+    assert np.max(np.abs(step[ok] - ref[ok])) < 5e-6 * max(1.0, float(np.abs(pts).max()))
+    reset_tuning(M)
 
 
 def test_esp_rsqrt_on_the_fma_pipe(M):
@@ -485,7 +542,7 @@ def test_field_grid_recognises_box_meshes(M, frame2a):
         M.set_tuning(k1_lattice=-1, k1_splits=1)
         auto = M.field_grid(pts, soften=True, concat=True)
         assert M.last_path() == "lattice", shape
-        M.set_tuning(k1_lattice=0, k1_splits=1, k1_points=4, k1_lanes=1)
+        M.set_tuning(k1_lattice=0, k1_splits=1, k1_points=4, k1_lanes=1, k1_hybrid=0)   # direct-form general kernel
         gen = M.field_grid(pts, soften=True, concat=True)
         assert M.last_path() == "general"
         np.testing.assert_array_equal(auto, gen)
@@ -504,7 +561,7 @@ def test_field_grid_recognises_box_meshes(M, frame2a):
         bumped = pts.copy()
         bumped[len(pts) // 2, 1] += np.float32(1e-4)
         got = M.field_grid(bumped, soften=True)
-        assert M.last_path() == "general"
+        assert M.last_path() in ("general", "general_hybrid")
         assert relmax(got, f64.field_grid(bumped, x, Q, True)) < FIELD_TOL
     # legacy symbol goes through the same host entry point
     axes = [np.linspace(-0.5, 0.5, 17, dtype=np.float32)] * 3

@@ -14,6 +14,11 @@ for M_ in (301, 20_000):                       # resident and streamed charge st
     pts = synth.grid(17, 0.5)                  # 4913 points: lattice path via auto-detection
     m.field_grid(pts, soften=True, concat=True)
     m.field_grid(pts[::-1][:1000].copy() + np.float32(0.001), soften=False)
+    rp = (np.random.default_rng(2).uniform(-0.5, 0.5, (2500, 3))).astype(np.float32)     # >= 2,048 points: hybrid near/far general kernel
+    m.field_grid(rp, soften=True, concat=True)
+    m.set_tuning(k1_splits=5)
+    m.field_grid(rp, soften=False)
+    m.set_tuning(k1_splits=0)
     m.esp_grid(pts[:777], concat_half=True)
     m.propagate(pts[:100], 0.1)
     for cfg in (dict(), dict(k1_lanes=8, k1_splits=3), dict(k1_lanes=32), dict(k1_points=2, k1_lanes=1, k1_tile_pairs=64, k1_stages=2)):

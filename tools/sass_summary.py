@@ -21,6 +21,8 @@ HOT = [
     ("k2p_topo_kernel<true, 6>", "K2 points-packed, second-difference curvature instantiation"),
     ("k2x_topo_kernel<false, 6, 4>", "K2 hybrid form with charge pairs packed (short queues)"),
     ("k2w_topo_kernel<false, 4, 4>", "K2 round-1 direct form (k2_form=1, kept for A/B)"),
+    ("k1x_grid_kernel<false>", "K1 general, hybrid near/far form (field sums over >= 2,048 listed points), raw"),
+    ("k1x_grid_kernel<true>", "K1 general, hybrid near/far form, softened (`volume` semantics on the near class)"),
     ("k1_grid_kernel<1, 4, 1>", "K1 general, raw field, 4 points per thread"),
     ("k1_grid_kernel<0, 4, 1>", "K1 general, softened field (`volume` on non-mesh point lists), 4 points per thread"),
     ("k1_grid_kernel<2, 2, 1>", "K1 general, ESP, 2 points per thread (esp101 default)"),
