@@ -100,3 +100,30 @@ def test_topo_hist_frames_argument_checks_need_no_device():
         m.topo_hist_frames(frames, seeds, np.ones((2, 5), np.int32), e, e)
     with pytest.raises(ValueError, match="rows but Q"):
         m.topo_hist_frames([(np.zeros((4, 3), np.float32), np.zeros(3, np.float32))], seeds, np.ones(5, np.int32), e, e)
+
+
+def test_gather_helpers_without_a_process_group():
+    """world_size 1: the gather helpers copy into the caller's buffer, keep the dtype, and reject a block whose length
+    disagrees with the plan; deal_lines_all partitions the lines and deals blocks in serpentine order."""
+    import pytest
+    import torch
+
+    rows = np.arange(12, dtype=np.int64).reshape(6, 2)
+    out = torch.empty((6, 2), dtype=torch.int64)
+    got = sharding.all_gather_blocks(rows, [6], out=out)
+    assert got is out and got.dtype == torch.int64 and np.array_equal(got.numpy(), rows)
+    with pytest.raises(ValueError):
+        sharding.all_gather_blocks(rows, [5])
+    with pytest.raises(ValueError):
+        sharding.all_gather_blocks(rows, [6], out=torch.empty((6, 2), dtype=torch.float32))
+    ax = np.linspace(-1, 1, 4)
+    full = sharding.lattice_sharded(lambda xs, ys, zs: np.stack(np.meshgrid(xs, ys, zs, indexing="ij"), -1).reshape(-1, 3), ax, ax, ax)
+    assert full.shape == (64, 3) and np.array_equal(full.numpy()[:, 2][:4], ax)          # z fastest
+    n_iter = np.random.RandomState(3).randint(1, 17, 1000)
+    deal = sharding.deal_lines_all(n_iter, 4)
+    assert sorted(np.concatenate(deal).tolist()) == list(range(1000))
+    order = np.argsort(-n_iter, kind="stable")
+    assert np.array_equal(deal[0][:32], order[:32]) and np.array_equal(deal[3][:32], order[96:128])
+    assert np.array_equal(deal[3][32:64], order[128:160])                                # second round runs backwards
+    work = [int(n_iter[d].sum()) for d in deal]
+    assert max(work) - min(work) <= 0.02 * np.mean(work)
